@@ -1,0 +1,123 @@
+"""Pins oracle/thrill_oracle.c against outputs of the UNMODIFIED reference:
+(1) the committed fixtures tests/golden/reference_outputs.npz (made by tests/golden/make_golden.py),
+(2) when the prebuilt reference binary is present (oracle/_ref/thrill_ref_driver), live runs on fresh inputs.
+CPU only."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from golden_util import REDUCE_OUT, golden, sha
+
+
+def _counts(n, p):
+    c = np.full(p, n // p, dtype=np.uint64)
+    c[: n % p] += 1
+    return c
+
+
+def test_golden_sort_uniform():
+    g = golden()
+    keys = O.gen_sort_uniform(0, 4096)
+    out, _ = O.sort_operator(keys, _counts(4096, 3))
+    assert np.array_equal(out.view(np.uint64), g["sort_uniform_4096_w3"])
+    keys = O.gen_sort_uniform(0, 1000000)
+    out, _ = O.sort_operator(keys, _counts(1000000, 4))
+    assert sha(out) == str(g["sort_uniform_1000000_w4_sha256"])
+
+
+def test_golden_sort_zipf_duplicates():
+    g = golden()
+    cdf = O.zipf_cdf(1024)
+    keys = O.gen_sort_zipf(0, 50000, cdf)
+    out, oc = O.sort_operator(keys, _counts(50000, 5))
+    out = out.view(np.uint64)
+    assert np.array_equal(out[:64], g["sort_zipf_u1024_50000_w5_head"])
+    assert sha(out) == str(g["sort_zipf_u1024_50000_w5_sha256"])
+
+
+def test_golden_reduce_f64_zipf_tolerance_and_ownership():
+    g = golden()
+    ref = g["reduce_f64_zipf_u4096_200000_w3"]
+    cdf = O.zipf_cdf(4096)
+    kv = O.gen_reduce_zipf(0, 200000, cdf)
+    out, oc = O.reduce_operator(kv, _counts(200000, 3), 64 << 20, O.OP_SUM_F64)
+    owner = np.repeat(np.arange(3, dtype=np.uint64), oc.astype(np.int64))
+    order = np.argsort(out["key"], kind="stable")
+    out, owner = out[order], owner[order]
+    assert np.array_equal(out["key"], ref["key"])
+    # same owner worker as the reference: key -> Hash128to64(0,key) % p
+    assert np.array_equal(owner, ref["worker"])
+    a, b = out["val"].view(np.float64), ref["val"].view(np.float64)
+    assert np.all(np.abs(a - b) <= 1e-9 * np.maximum(1.0, np.abs(b)))      # SURVEY.md §8d tolerance
+
+
+def test_golden_reduce_exact_modes_bit_identical():
+    g = golden()
+    ref = g["reduce_f64_exact_zipf_u4096_200000_w4"]
+    cdf = O.zipf_cdf(4096)
+    kv = O.gen_reduce_zipf(0, 200000, cdf, exact=1)
+    out, oc = O.reduce_operator(kv, _counts(200000, 4), 64 << 20, O.OP_SUM_F64)
+    out = np.sort(out, order="key")
+    assert np.array_equal(out["key"], ref["key"]) and np.array_equal(out["val"], ref["val"])
+    ref = g["reduce_u64_uniform_u3000_100000_w2"]
+    kv = O.gen_reduce_uniform(0, 100000, universe=3000, exact=2)
+    out, oc = O.reduce_operator(kv, _counts(100000, 2), 64 << 20, O.OP_SUM_U64)
+    out = np.sort(out, order="key")
+    assert np.array_equal(out["key"], ref["key"]) and np.array_equal(out["val"], ref["val"])
+    # and the simple checker agrees with the faithful table restatement
+    simple = O.reduce_simple(kv, O.OP_SUM_U64)
+    assert np.array_equal(simple, out)
+
+
+def test_golden_terasort_records():
+    g = golden()
+    rec = O.gen_records(0, 20000)
+    out, _ = O.sort_operator(rec, _counts(20000, 3), desc=O.RECORD_DESC)
+    out = out.reshape(-1, 100)
+    assert np.array_equal(out[:8], g["terasort_20000_w3_head"])
+    assert sha(out) == str(g["terasort_20000_w3_sha256"])
+
+
+# ---- live runs of the reference itself (binary prebuilt in oracle/_ref; skipped if absent) ----
+needs_ref = pytest.mark.skipif(not O.have_ref_driver(), reason="oracle/_ref/thrill_ref_driver not built")
+
+
+@needs_ref
+@pytest.mark.ref
+@pytest.mark.parametrize("workers,n", [(1, 30000), (2, 1), (3, 12345), (8, 200000)])
+def test_live_reference_sort_file_input(workers, n):
+    rng = np.random.RandomState(workers * 1000 + n % 997)
+    keys = rng.randint(0, 50, size=n).astype(np.uint64) if workers == 3 else \
+        rng.randint(0, 2**63, size=n).astype(np.uint64)
+    with tempfile.TemporaryDirectory() as d:
+        keys.tofile(os.path.join(d, "in.bin"))
+        O.run_ref_driver(workers=workers, op="sort_u64", gen="file", out=os.path.join(d, "o.bin"),
+                         **{"in": os.path.join(d, "in.bin")})
+        ref = np.fromfile(os.path.join(d, "o.bin"), dtype=np.uint64)
+    out, _ = O.sort_operator(keys, _counts(n, workers))
+    assert np.array_equal(out.view(np.uint64), ref)
+
+
+@needs_ref
+@pytest.mark.ref
+@pytest.mark.parametrize("workers", [1, 2, 5])
+def test_live_reference_reduce_with_zero_key(workers):
+    rng = np.random.RandomState(workers)
+    n = 60000
+    kv = np.zeros(n, dtype=O.KV)
+    kv["key"] = rng.randint(0, 500, size=n)          # includes key 0: sentinel slot path
+    kv["val"] = rng.randint(0, 1000, size=n)
+    with tempfile.TemporaryDirectory() as d:
+        kv.tofile(os.path.join(d, "in.bin"))
+        O.run_ref_driver(workers=workers, op="reduce_u64", gen="file", out=os.path.join(d, "o.bin"),
+                         **{"in": os.path.join(d, "in.bin")})
+        ref = np.sort(np.fromfile(os.path.join(d, "o.bin"), dtype=REDUCE_OUT), order="key")
+    out, oc = O.reduce_operator(kv, _counts(n, workers), 64 << 20, O.OP_SUM_U64)
+    owner = np.repeat(np.arange(workers, dtype=np.uint64), oc.astype(np.int64))
+    order = np.argsort(out["key"], kind="stable")
+    assert np.array_equal(out["key"][order], ref["key"])
+    assert np.array_equal(out["val"][order], ref["val"])
+    assert np.array_equal(owner[order], ref["worker"])
