@@ -1,0 +1,227 @@
+// tg_ctx.cu — context, device memory, File<->device codec, timers (C ABI: include/thrill_gpu.h)
+#include <stdarg.h>
+
+#include "tg_common.cuh"
+
+int tg_set_error(tg_ctx* ctx, int status, const char* fmt, ...) {
+    if (ctx) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+        va_end(ap);
+    }
+    return status;
+}
+
+int tg_ws_get(tg_ctx* ctx, int slot, size_t bytes, void** out) {
+    if (bytes == 0) bytes = 256;
+    if (ctx->ws_bytes[slot] < bytes) {
+        if (ctx->ws[slot]) {
+            TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            TG_CUDA(ctx, cudaFree(ctx->ws[slot]));
+            ctx->ws[slot] = nullptr;
+            ctx->ws_bytes[slot] = 0;
+        }
+        size_t want = bytes + (bytes >> 3) + 4096;      // head-room so slowly growing sizes don't realloc
+        cudaError_t e = cudaMalloc(&ctx->ws[slot], want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            want = bytes;
+            e = cudaMalloc(&ctx->ws[slot], want);
+        }
+        if (e != cudaSuccess)
+            return tg_set_error(ctx, TG_ERR_OOM, "workspace slot %d: cudaMalloc(%zu) -> %s", slot, want, cudaGetErrorString(e));
+        ctx->ws_bytes[slot] = want;
+    }
+    *out = ctx->ws[slot];
+    return TG_OK;
+}
+
+extern "C" {
+
+int tg_version(void) { return 100; }
+
+const char* tg_strerror(int status) {
+    switch (status) {
+    case TG_OK: return "ok";
+    case TG_ERR_CUDA: return "CUDA error";
+    case TG_ERR_NCCL: return "NCCL error";
+    case TG_ERR_ARG: return "bad argument / unsupported descriptor";
+    case TG_ERR_TOO_LARGE: return "too many items for one call";
+    case TG_ERR_NO_DEVICE: return "no sm_100 CUDA device (there is no CPU fallback)";
+    case TG_ERR_OOM: return "out of device memory";
+    default: return "unknown status";
+    }
+}
+
+const char* tg_last_error(const tg_ctx* ctx) { return ctx ? ctx->err : "no context"; }
+
+int tg_get_unique_id(void* out128) {
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    if (ncclGetUniqueId(&id) != ncclSuccess) return TG_ERR_NCCL;
+    memcpy(out128, &id, sizeof(id));
+    return TG_OK;
+}
+
+int tg_init(int device, int rank, int nranks, const void* unique_id128, tg_ctx** out_ctx) {
+    if (!out_ctx || nranks < 1 || rank < 0 || rank >= nranks) return TG_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return TG_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= ndev) return TG_ERR_ARG;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return TG_ERR_CUDA;
+    if (prop.major != 10) return TG_ERR_NO_DEVICE;      // kernels are built for sm_100a only
+    tg_ctx* ctx = new tg_ctx();
+    ctx->device = device; ctx->rank = rank; ctx->nranks = nranks;
+    ctx->sm_count = prop.multiProcessorCount;
+    *out_ctx = ctx;
+    TG_CUDA(ctx, cudaSetDevice(device));
+    TG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    TG_CUDA(ctx, cudaEventCreate(&ctx->ev_start));
+    TG_CUDA(ctx, cudaEventCreate(&ctx->ev_stop));
+    ctx->pinned_bytes = 1 << 20;
+    TG_CUDA(ctx, cudaMallocHost(&ctx->pinned, ctx->pinned_bytes));
+    if (nranks > 1) {
+        if (!unique_id128) return tg_set_error(ctx, TG_ERR_ARG, "nranks > 1 needs a unique id");
+        ncclUniqueId id;
+        memcpy(&id, unique_id128, sizeof(id));
+        TG_NCCL(ctx, ncclCommInitRank(&ctx->comm, nranks, id, rank));
+    }
+    return TG_OK;
+}
+
+int tg_shutdown(tg_ctx* ctx) {
+    if (!ctx) return TG_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm) ncclCommDestroy(ctx->comm);
+    for (auto& kv : ctx->allocs) cudaFree(kv.first);
+    for (int i = 0; i < TG_NUM_WS; ++i)
+        if (ctx->ws[i]) cudaFree(ctx->ws[i]);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+    if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return TG_OK;
+}
+
+int tg_rank(const tg_ctx* ctx) { return ctx->rank; }
+int tg_nranks(const tg_ctx* ctx) { return ctx->nranks; }
+void* tg_stream(const tg_ctx* ctx) { return (void*)ctx->stream; }
+uint64_t tg_launch_count(const tg_ctx* ctx) { return ctx->launches; }
+
+int tg_sync(tg_ctx* ctx) {
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TG_OK;
+}
+
+int tg_barrier(tg_ctx* ctx) {
+    if (ctx->nranks > 1) {
+        void* d;
+        TG_TRY(tg_ws_get(ctx, WS_MISC, 4096, &d));
+        TG_CUDA(ctx, cudaMemsetAsync(d, 0, 8, ctx->stream));
+        TG_NCCL(ctx, ncclAllReduce(d, d, 1, ncclInt32, ncclSum, ctx->comm, ctx->stream));
+    }
+    return tg_sync(ctx);
+}
+
+int tg_alloc(tg_ctx* ctx, size_t bytes, void** out_dptr) {
+    if (!out_dptr) return TG_ERR_ARG;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 256);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return tg_set_error(ctx, TG_ERR_OOM, "cudaMalloc(%zu) -> %s", bytes, cudaGetErrorString(e));
+    }
+    ctx->allocs[p] = bytes;
+    *out_dptr = p;
+    return TG_OK;
+}
+
+int tg_free(tg_ctx* ctx, void* dptr) {
+    if (!dptr) return TG_OK;
+    auto it = ctx->allocs.find(dptr);
+    if (it == ctx->allocs.end()) return tg_set_error(ctx, TG_ERR_ARG, "tg_free of a pointer this ctx does not own");
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    TG_CUDA(ctx, cudaFree(dptr));
+    ctx->allocs.erase(it);
+    return TG_OK;
+}
+
+int tg_timer_start(tg_ctx* ctx) {
+    TG_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+    return TG_OK;
+}
+
+int tg_timer_stop(tg_ctx* ctx, float* out_ms) {
+    TG_CUDA(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
+    TG_CUDA(ctx, cudaEventSynchronize(ctx->ev_stop));
+    TG_CUDA(ctx, cudaEventElapsedTime(out_ms, ctx->ev_start, ctx->ev_stop));
+    return TG_OK;
+}
+
+int tg_upload(tg_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+    if (bytes) TG_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return TG_OK;
+}
+
+int tg_download(tg_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+    if (bytes) TG_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return TG_OK;
+}
+
+int tg_upload_blocks(tg_ctx* ctx, void* dst_dev, const tg_block* blocks, size_t nblocks, size_t* out_bytes) {
+    size_t off = 0;
+    for (size_t i = 0; i < nblocks; ++i) {
+        if (blocks[i].bytes)
+            TG_CUDA(ctx, cudaMemcpyAsync((char*)dst_dev + off, blocks[i].data, blocks[i].bytes,
+                                         cudaMemcpyHostToDevice, ctx->stream));
+        off += blocks[i].bytes;
+    }
+    if (out_bytes) *out_bytes = off;
+    return TG_OK;
+}
+
+int tg_download_blocks(tg_ctx* ctx, const void* src_dev, const tg_block_mut* blocks, size_t nblocks) {
+    size_t off = 0;
+    for (size_t i = 0; i < nblocks; ++i) {
+        if (blocks[i].bytes)
+            TG_CUDA(ctx, cudaMemcpyAsync(blocks[i].data, (const char*)src_dev + off, blocks[i].bytes,
+                                         cudaMemcpyDeviceToHost, ctx->stream));
+        off += blocks[i].bytes;
+    }
+    return TG_OK;
+}
+
+// data/block_writer.hpp:61-67 (initial block size), :405-420 (doubling), :183-203 / :339-372 (item starts,
+// straddling Append) for fixed-size items
+size_t tg_file_geometry(uint64_t num_items, uint32_t item_bytes, uint64_t start_block_size,
+                        uint64_t max_block_size, tg_block_geom* out, size_t capacity) {
+    uint64_t total = num_items * (uint64_t)item_bytes;
+    uint64_t bs = start_block_size < max_block_size ? start_block_size : max_block_size;
+    uint64_t pos = 0;
+    size_t nb = 0;
+    while (pos < total) {
+        uint64_t len = total - pos < bs ? total - pos : bs;
+        // first item starting at/after pos, items starting inside [pos, pos+len)
+        uint64_t first_idx = (pos + item_bytes - 1) / item_bytes;
+        uint64_t end_idx = (pos + len + item_bytes - 1) / item_bytes;     // first item starting at/after block end
+        if (end_idx > num_items) end_idx = num_items;
+        if (nb < capacity) {
+            out[nb].bytes = len;
+            out[nb].num_items = end_idx > first_idx ? end_idx - first_idx : 0;
+            out[nb].first_item = out[nb].num_items ? first_idx * item_bytes - pos : 0;
+        }
+        ++nb;
+        pos += len;
+        if (2 * bs < max_block_size) bs *= 2;
+    }
+    return nb;
+}
+
+}  // extern "C"

@@ -1,0 +1,123 @@
+// tg_radix_sort.cu — LSB radix sort of fixed-size items on one B200 (sm_100a).
+//
+// Replaces the local sort of the reference's sample sort: SortNode::SortAndWriteToFile ->
+// sort_algorithm_(begin,end,cmp) = std::sort (api/sort.hpp:696-742, :789-796).
+//
+// One histogram kernel (all digit histograms from a single read of the input), one tiny scan kernel,
+// then one stable partition pass (tg_partition.cuh, "onesweep") per 8-bit digit, least significant
+// first.  Digit positions where every key has the same value are skipped (identity passes).
+// HBM traffic: n*s for the histogram + per executed pass n*s read + n*s write (s = item bytes).
+#include "tg_partition.cuh"
+
+using namespace tgp;
+
+namespace {
+
+constexpr int MAX_PASSES = 16;
+
+struct PassList {
+    int npass;
+    unsigned char word[MAX_PASSES];     // which u64 word of the item holds the digit
+    unsigned char shift[MAX_PASSES];    // bit shift inside the word
+    u32 flip;                           // RADIX-1 for descending order
+};
+
+// histogram of every digit position from one read of the input
+template <int WORDS>
+__global__ void __launch_bounds__(512) radix_hist_kernel(const typename ItemT<WORDS>::type* __restrict__ in, size_t n,
+                                                         PassList pl, u32* __restrict__ ghist) {
+    extern __shared__ u32 sh[];      // [npass][RADIX]
+    for (int i = threadIdx.x; i < pl.npass * RADIX; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t base = (size_t)blockIdx.x * blockDim.x; base < n; base += stride) {
+        size_t i = base + threadIdx.x;
+        bool valid = i < n;
+        typename ItemT<WORDS>::type v;
+        if (valid) v = in[i];
+        u32 act = __ballot_sync(0xffffffffu, valid);
+        if (!valid) continue;
+#pragma unroll 1
+        for (int p = 0; p < pl.npass; ++p) {
+            u32 d = ((u32)(item_word(v, pl.word[p]) >> pl.shift[p]) & (RADIX - 1)) ^ pl.flip;
+            // heavily duplicated digit positions (constant high bytes, Zipf keys): one atomic per warp
+            u32 d0 = __shfl_sync(act, d, __ffs(act) - 1);
+            if (__all_sync(act, d == d0)) {
+                if (lane_id() == (u32)(__ffs(act) - 1)) atomicAdd(&sh[p * RADIX + d], __popc(act));
+            }
+            else atomicAdd(&sh[p * RADIX + d], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < pl.npass * RADIX; i += blockDim.x)
+        if (sh[i]) atomicAdd(&ghist[i], sh[i]);
+}
+
+// digit passes of a key descriptor over the item's little-endian u64 words, least significant first
+int build_pass_list(const tg_key_desc* d, PassList* pl) {
+    if (d->item_bytes != 8 && d->item_bytes != 16) return TG_ERR_ARG;
+    if (d->key_bytes == 0 || d->key_bytes > MAX_PASSES || d->key_offset + d->key_bytes > d->item_bytes) return TG_ERR_ARG;
+    pl->npass = (int)d->key_bytes;
+    pl->flip = d->descending ? (RADIX - 1) : 0;
+    for (u32 j = 0; j < d->key_bytes; ++j) {
+        u32 byte = (d->key_kind == TG_KEY_UINT_LE) ? d->key_offset + j : d->key_offset + d->key_bytes - 1 - j;
+        pl->word[j] = (unsigned char)(byte / 8);
+        pl->shift[j] = (unsigned char)(8 * (byte % 8));
+    }
+    return TG_OK;
+}
+
+template <int WORDS>
+int radix_sort_impl(tg_ctx* ctx, const PassList& pl, void* d_items, void* d_tmp, size_t n) {
+    typedef typename ItemT<WORDS>::type Item;
+    const u32 num_tiles = num_tiles_for<WORDS>(n);
+
+    u32* hist;      // [npass][RADIX] counts | [npass][RADIX] bases | [npass] skip
+    size_t hist_words = (size_t)2 * pl.npass * RADIX + MAX_PASSES;
+    TG_TRY(tg_ws_get(ctx, WS_SORT_HIST, hist_words * 4, (void**)&hist));
+    u32* gbase = hist + (size_t)pl.npass * RADIX;
+    u32* skip = gbase + (size_t)pl.npass * RADIX;
+    u32* status;
+    size_t status_bytes = (size_t)pl.npass * num_tiles * RADIX * 4;
+    TG_TRY(tg_ws_get(ctx, WS_SORT_STATUS, status_bytes, (void**)&status));
+    TG_CUDA(ctx, cudaMemsetAsync(hist, 0, hist_words * 4, ctx->stream));
+    TG_CUDA(ctx, cudaMemsetAsync(status, 0, status_bytes, ctx->stream));
+
+    TG_LAUNCH(ctx, radix_hist_kernel<WORDS>, ctx->sm_count * 2, 512, pl.npass * RADIX * 4, (const Item*)d_items, n, pl, hist);
+    TG_LAUNCH(ctx, scan_hist_kernel, 1, RADIX, 0, hist, gbase, skip, pl.npass, (u32)n);
+    u32* h_skip = (u32*)ctx->pinned;
+    TG_CUDA(ctx, cudaMemcpyAsync(h_skip, skip, pl.npass * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+
+    void* src = d_items;
+    void* dst = d_tmp;
+    for (int p = 0; p < pl.npass; ++p) {
+        if (h_skip[p]) continue;       // every key has the same digit here: the pass is the identity
+        RadixDigit fn = { (int)pl.word[p], (int)pl.shift[p], pl.flip };
+        TG_TRY((launch_partition<WORDS, RadixDigit>(ctx, src, dst, (u32)n, fn, gbase + (size_t)p * RADIX,
+                                                    status + (size_t)p * num_tiles * RADIX)));
+        void* t = src; src = dst; dst = t;
+    }
+    if (src != d_items)
+        TG_LAUNCH(ctx, copy_items_kernel<WORDS>, ctx->sm_count * 8, 256, 0, (const Item*)src, (Item*)d_items, n);
+    return TG_OK;
+}
+
+}  // namespace
+
+// used by the operators (tg_sample_sort.cu): result in d_items
+int tg_radix_sort_items(tg_ctx* ctx, const tg_key_desc* desc, void* d_items, void* d_tmp, size_t n) {
+    if (n >= (1u << 30)) return tg_set_error(ctx, TG_ERR_TOO_LARGE, "radix sort: n=%zu >= 2^30", n);
+    if (((uintptr_t)d_items | (uintptr_t)d_tmp) & 15) return tg_set_error(ctx, TG_ERR_ARG, "buffers must be 16-byte aligned");
+    PassList pl;
+    if (build_pass_list(desc, &pl) != TG_OK) return tg_set_error(ctx, TG_ERR_ARG, "radix sort: unsupported key descriptor");
+    if (n < 2) return TG_OK;
+    return desc->item_bytes == 8 ? radix_sort_impl<1>(ctx, pl, d_items, d_tmp, n)
+                                 : radix_sort_impl<2>(ctx, pl, d_items, d_tmp, n);
+}
+
+extern "C" int tg_radix_sort_local(tg_ctx* ctx, const tg_key_desc* desc, void* d_items, void* d_tmp, size_t n) {
+    if (!ctx || !desc) return TG_ERR_ARG;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    return tg_radix_sort_items(ctx, desc, d_items, d_tmp, n);
+}
