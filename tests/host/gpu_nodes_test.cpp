@@ -1,0 +1,98 @@
+/*******************************************************************************
+ * tests/host/gpu_nodes_test.cpp — integration test of the drop-in INSIDE the unmodified reference.
+ *
+ * A real Thrill job (api::Run, mock network, THRILL_WORKERS_PER_HOST = number of GPUs): the same DIAs go
+ * through the stock CPU operators (dia.Sort(), dia.ReducePair()) and through the GPU nodes of
+ * thrill_b200/host/thrill_gpu_nodes.hpp (thrill_gpu::Sort, thrill_gpu::ReducePair); the gathered results must
+ * be identical (bit-exact order for Sort; same key set and exact sums for ReducePair in the integer-valued
+ * double mode).  Mirrors tests/api/sort_node_test.cpp and tests/api/reduce_node_test.cpp of the reference.
+ * Links the reference library built by oracle/ref/Makefile (it IS the rest of the pipeline) and
+ * libthrill_gpu.so.  Prints "PASS ..." lines and exits non-zero on any mismatch.
+ ******************************************************************************/
+#include <thrill/api/all_gather.hpp>
+#include <thrill/api/cache.hpp>
+#include <thrill/api/generate.hpp>
+#include <thrill/api/reduce_by_key.hpp>
+#include <thrill/api/size.hpp>
+#include <thrill/api/sort.hpp>
+#include <thrill/common/stats_timer.hpp>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <utility>
+#include <vector>
+
+#include "../../thrill_b200/host/thrill_gpu_nodes.hpp"
+
+using namespace thrill; // NOLINT
+
+static inline uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+static std::atomic<int> g_failures { 0 };
+
+int main(int argc, char** argv) {
+    size_t n = argc > 1 ? strtoull(argv[1], nullptr, 10) : 2000000;
+    int rc = api::Run(
+        [&](api::Context& ctx) {
+            // ---- Sort: uniform keys, then heavy duplicates (tie-break path), then empty ----
+            for (int variant = 0; variant < 3; ++variant) {
+                size_t nn = variant == 2 ? 0 : n;
+                auto input = api::Generate(ctx, nn, [variant](size_t i) -> uint64_t {
+                                               uint64_t r = splitmix64(i + 42);
+                                               return variant == 1 ? r % 7 : r;
+                                           }).Cache().Keep(2);
+                common::StatsTimerStart t_cpu;
+                std::vector<uint64_t> cpu = input.Sort().AllGather();
+                t_cpu.Stop();
+                common::StatsTimerStart t_gpu;
+                std::vector<uint64_t> gpu = thrill_gpu::Sort(input).AllGather();
+                t_gpu.Stop();
+                bool ok = cpu == gpu && cpu.size() == nn;
+                if (ctx.my_rank() == 0)
+                    printf("%s Sort variant=%d n=%zu workers=%zu cpu=%.3fs gpu=%.3fs\n", ok ? "PASS" : "FAIL",
+                           variant, nn, ctx.num_workers(), t_cpu.SecondsDouble(), t_gpu.SecondsDouble());
+                if (!ok) g_failures++;
+            }
+            // ---- ReducePair<uint64_t,double>(plus), integer-valued doubles => exact sums; includes key 0 ----
+            {
+                using Pair = std::pair<uint64_t, double>;
+                auto input = api::Generate(ctx, n, [](size_t i) {
+                                               uint64_t r = splitmix64(i + 7);
+                                               return Pair(r % 50021, static_cast<double>(splitmix64(i) % 1024));
+                                           }).Cache().Keep(2);
+                auto by_key = [](const Pair& a, const Pair& b) { return a.first < b.first; };
+                std::vector<Pair> cpu = input.ReducePair(std::plus<double>()).AllGather();
+                std::vector<Pair> gpu = thrill_gpu::ReducePair(input, std::plus<double>()).AllGather();
+                std::sort(cpu.begin(), cpu.end(), by_key);
+                std::sort(gpu.begin(), gpu.end(), by_key);
+                bool ok = cpu == gpu;
+                if (ctx.my_rank() == 0)
+                    printf("%s ReducePair n=%zu distinct=%zu workers=%zu\n", ok ? "PASS" : "FAIL", n, cpu.size(), ctx.num_workers());
+                if (!ok) g_failures++;
+            }
+            // ---- Sort feeding ReducePair (GPU node -> GPU node through PushFile / OnPreOpFile) ----
+            {
+                using Pair = std::pair<uint64_t, uint64_t>;
+                auto pairs = api::Generate(ctx, n, [](size_t i) { return Pair(splitmix64(i) % 1000, i % 13); }).Cache().Keep(2);
+                std::vector<Pair> cpu = pairs.ReducePair(std::plus<uint64_t>()).AllGather();
+                std::vector<Pair> gpu = thrill_gpu::ReducePair(
+                    thrill_gpu::Sort(pairs, thrill_gpu::LessFirst()), std::plus<uint64_t>()).AllGather();
+                std::sort(cpu.begin(), cpu.end());
+                std::sort(gpu.begin(), gpu.end());
+                bool ok = cpu == gpu;
+                if (ctx.my_rank() == 0) printf("%s SortStable->ReducePair chain n=%zu\n", ok ? "PASS" : "FAIL", n);
+                if (!ok) g_failures++;
+            }
+        });
+    if (rc != 0) return rc;
+    return g_failures.load() ? 1 : 0;
+}

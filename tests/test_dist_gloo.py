@@ -1,0 +1,137 @@
+"""world_size-2 (and 3) CPU tests over gloo of the host logic on the N>1 path: the control-plane arithmetic the
+GPU operator performs around its kernels (shard ranges, sample counts, identical splitter selection on every
+rank from all-gathered samples, count exchange -> Alltoallv offsets) with the per-rank compute done by the
+oracle (test infrastructure).  The distributed result must equal the output of the unmodified reference
+(tests/golden).  Also covers bench.py's cross-rank reductions."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _init(rank, world, port):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    for p in (ROOT, HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+
+def _all_gather(arr, world):
+    parts = [None] * world
+    dist.all_gather_object(parts, arr)
+    return parts
+
+
+def _sort_worker(rank, world, port, n, out_dir):
+    _init(rank, world, port)
+    import oracle_lib as O
+    from thrill_b200 import api, capi
+    L = capi.lib()
+    # shard exactly as api.Generate / common::CalculateLocalRange does
+    lo, hi = api._local_range(n, world, rank)
+    keys = O.gen_sort_uniform(lo, hi - lo)
+    n_local = hi - lo
+    # (1) ExPrefixSumTotal
+    counts = [int(x[0]) for x in _all_gather(np.array([n_local], dtype=np.uint64), world)]
+    prefix = sum(counts[:rank])
+    assert prefix == lo
+    # (2) samples (item, global index), all-gathered; every rank selects the same splitters with the C ABI
+    ns = min(n_local, L.tg_sample_size(n_local))
+    rng = np.random.RandomState(1000 + rank)
+    idx = rng.randint(0, n_local, size=ns)
+    mine = O.pack_samples(keys[idx], (idx + prefix).astype(np.uint64))
+    allsamp = np.ascontiguousarray(np.concatenate(_all_gather(mine, world)))
+    spl = np.zeros((world - 1, 16), dtype=np.uint8)
+    d = capi.u64_desc()
+    assert L.tg_select_splitters(C.byref(d), allsamp.ctypes.data, len(allsamp), world, spl.ctypes.data) == 0
+    all_spl = _all_gather(spl, world)
+    assert all(np.array_equal(all_spl[0], s) for s in all_spl)          # identical on every rank
+    # (3) classify (oracle = checker standing in for the CUDA kernel), count exchange, Alltoallv
+    padded, k = O.pad_splitters(spl, world)
+    tree = O.build_tree(padded, k)
+    b = O.classify(keys, prefix, tree, k, padded).astype(np.int64)
+    b[b == k - 1] = world - 1
+    send = [np.ascontiguousarray(keys[b == r]) for r in range(world)]
+    send_cnt = np.array([len(s) for s in send], dtype=np.int64)
+    mat = np.stack(_all_gather(send_cnt, world))                        # [src][dst]
+    recv_cnt = mat[:, rank]
+    # gloo has no all_to_all: exchange through all_gather_object (test-scale data)
+    allsend = _all_gather(send, world)
+    got = [allsend[src][rank] for src in range(world)]
+    assert [len(g) for g in got] == [int(c) for c in recv_cnt]
+    cat = np.concatenate(got)
+    local_sorted = O.sort_items(cat).view(np.uint64) if len(cat) else np.empty(0, np.uint64)
+    np.save(os.path.join(out_dir, "part%d.npy" % rank), local_sorted)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_distributed_sample_sort_host_logic_matches_reference(tmp_path, world):
+    from golden_util import golden
+    n = 4096
+    port = 29511 + world
+    mp.spawn(_sort_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
+    out = np.concatenate([np.load(os.path.join(str(tmp_path), "part%d.npy" % r)) for r in range(world)])
+    assert np.array_equal(out, golden()["sort_uniform_4096_w3"])          # same generator, same global result
+
+
+def _reduce_worker(rank, world, port, out_dir):
+    _init(rank, world, port)
+    import oracle_lib as O
+    from thrill_b200 import api
+    n = 200000
+    lo, hi = api._local_range(n, world, rank)
+    cdf = O.zipf_cdf(4096)
+    kv = O.gen_reduce_zipf(lo, hi - lo, cdf, exact=1)
+    pre, part = O.reduce_pre_phase(kv, world, 32 << 20, O.OP_SUM_F64)       # partition = Hash128to64(0,key) % p
+    send = [np.ascontiguousarray(pre[part == r]) for r in range(world)]
+    allsend = _all_gather(send, world)
+    got = np.concatenate([allsend[src][rank] for src in range(world)])
+    out, _ = O.reduce_post_phase(got, 32 << 20, O.OP_SUM_F64)
+    np.save(os.path.join(out_dir, "red%d.npy" % rank), out)
+    # bench.py's cross-rank reductions over gloo
+    import bench
+    assert bench.max_over_ranks(float(rank + 1), world) == float(world)
+    assert bench.sum_over_ranks(1.0, world) == float(world)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_distributed_reduce_host_logic_matches_reference(tmp_path):
+    import oracle_lib as O
+    from golden_util import golden
+    world = 2
+    mp.spawn(_reduce_worker, args=(world, 29530, str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(os.path.join(str(tmp_path), "red%d.npy" % r)) for r in range(world)]
+    for r, p in enumerate(parts):                                          # ownership: key -> hash % p
+        assert np.all(O.hash_partition_ids(p["key"], world) == r)
+    out = np.sort(np.concatenate(parts), order="key")
+    ref = golden()["reduce_f64_exact_zipf_u4096_200000_w4"]               # exact mode: independent of p
+    assert np.array_equal(out["key"], ref["key"]) and np.array_equal(out["val"], ref["val"])
+
+
+def test_local_range_matches_thrill_generate_split():
+    from thrill_b200 import api
+    for n in [0, 1, 7, 100, 4096, 10**8]:
+        for p in [1, 2, 3, 5, 8]:
+            r = [api._local_range(n, p, i) for i in range(p)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[i][1] == r[i + 1][0] for i in range(p - 1))
+            assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+
+
+def test_bench_zipf_table_equals_oracle_table():
+    import bench
+    import oracle_lib as O
+    assert np.array_equal(bench.zipf_cdf_numpy(4096), O.zipf_cdf(4096))
+    assert np.array_equal(bench.zipf_cdf_numpy(1 << 16), O.zipf_cdf(1 << 16))

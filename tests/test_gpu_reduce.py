@@ -1,0 +1,132 @@
+"""GPU parity of the ReduceByKey kernels against the oracle and the golden outputs of the unmodified
+reference: hash partition (bit-exact destinations, stable), hash aggregate (keys exact; values exact for
+integer ops and the exact-mode doubles, rel 1e-9 for f64 sums — SURVEY.md §8d).  pytest -m gpu."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from golden_util import golden
+from gpu_util import make_blocks, u64p
+
+pytestmark = pytest.mark.gpu
+F64_RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from thrill_b200 import capi
+    c = capi.Ctx(device=0)
+    yield c
+    c.close()
+
+
+def _aggregate(ctx, kv, op):
+    from thrill_b200 import capi
+    n = len(kv)
+    d_in = ctx.to_device(kv) if n else ctx.alloc(16)
+    d_out = ctx.alloc(max(n * 16, 16) + 32)
+    nd = C.c_uint64()
+    ctx.ck(ctx.L.tg_hash_aggregate(ctx.h, C.byref(capi.KVDesc(16, op)), d_in, n, d_out, C.byref(nd)))
+    out = ctx.download(d_out, nd.value * 16, O.KV)
+    ctx.free(d_in); ctx.free(d_out)
+    return np.sort(out, order="key")
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 8, 13])
+def test_hash_partition_bit_exact_and_stable(ctx, p):
+    from thrill_b200 import capi
+    n = 400003
+    kv = O.gen_reduce_uniform(0, n, universe=1 << 20, exact=2)
+    kv["key"][::1000] = 0                                              # the sentinel key hashes like any other
+    dest = O.hash_partition_ids(kv["key"], p).astype(np.int64)         # Hash128to64(0,key) % p
+    order = np.argsort(dest, kind="stable")
+    d_in = ctx.to_device(kv); d_out = ctx.alloc(n * 16)
+    oc = np.zeros(p, dtype=np.uint64)
+    ctx.ck(ctx.L.tg_hash_partition(ctx.h, C.byref(capi.KVDesc(16, capi.OP_SUM_U64)), d_in, n, p, d_out, u64p(oc)))
+    out = ctx.download(d_out, n * 16, O.KV)
+    assert np.array_equal(oc.astype(np.int64), np.bincount(dest, minlength=p))
+    assert np.array_equal(out, kv[order])
+    ctx.free(d_in); ctx.free(d_out)
+
+
+def test_hash_aggregate_reference_kats(ctx):
+    """tests/core/reduce_hash_table_test.cpp:54-144 (500 keys incl. key 0) and
+    tests/api/reduce_node_test.cpp:93-139 (1e6 pairs, 1000 keys)"""
+    from thrill_b200 import capi
+    i = np.arange(50000, dtype=np.uint64)
+    kv = np.zeros(50000, dtype=O.KV); kv["key"] = i % 500; kv["val"] = i // 500
+    out = _aggregate(ctx, kv, capi.OP_SUM_U64)
+    assert np.array_equal(out["key"], np.arange(500, dtype=np.uint64)) and np.all(out["val"] == 100 * 99 // 2)
+    i = np.arange(1000000, dtype=np.uint64)
+    kv = np.zeros(1000000, dtype=O.KV); kv["key"] = i % 1000; kv["val"] = i // 1000
+    out = _aggregate(ctx, kv, capi.OP_SUM_U64)
+    assert len(out) == 1000 and np.all(out["val"] == 1000 * 999 // 2)
+
+
+@pytest.mark.parametrize("n", [0, 1, 5, 4096, 200000])
+@pytest.mark.parametrize("op", ["sum_u64", "min_u64", "max_u64", "sum_f64_exact", "min_f64", "max_f64"])
+def test_hash_aggregate_ops_vs_oracle(ctx, n, op):
+    from thrill_b200 import capi
+    rng = np.random.RandomState(n + len(op))
+    kv = np.zeros(n, dtype=O.KV)
+    kv["key"] = rng.randint(0, max(2, n // 7), size=n)                 # includes the zero key
+    if op.endswith("u64"):
+        kv["val"] = rng.randint(0, 1 << 40, size=n)
+    elif op == "sum_f64_exact":
+        kv["val"] = rng.randint(0, 1024, size=n).astype(np.float64).view(np.uint64)
+    else:
+        kv["val"] = (rng.rand(n) * 100 - 50).view(np.uint64)
+    code = {"sum_u64": capi.OP_SUM_U64, "min_u64": capi.OP_MIN_U64, "max_u64": capi.OP_MAX_U64,
+            "sum_f64_exact": capi.OP_SUM_F64, "min_f64": capi.OP_MIN_F64, "max_f64": capi.OP_MAX_F64}[op]
+    ocode = {"sum_u64": O.OP_SUM_U64, "min_u64": O.OP_MIN_U64, "max_u64": O.OP_MAX_U64,
+             "sum_f64_exact": O.OP_SUM_F64, "min_f64": O.OP_MIN_F64, "max_f64": O.OP_MAX_F64}[op]
+    out = _aggregate(ctx, kv, code)
+    ref = O.reduce_simple(kv, ocode) if n else np.empty(0, dtype=O.KV)
+    assert np.array_equal(out, ref)
+
+
+def test_reduce_operator_golden_zipf_f64(ctx):
+    """cfg3 shape (reduced): ReducePair<u64,double>(plus) on Zipf keys vs the unmodified reference's output"""
+    from thrill_b200 import capi
+    g = golden()
+    ref = g["reduce_f64_zipf_u4096_200000_w3"]
+    kv = O.gen_reduce_zipf(0, 200000, O.zipf_cdf(4096))
+    blocks, nb, raw = make_blocks(capi, kv, 1 << 20)
+    n_out = C.c_size_t()
+    ctx.ck(ctx.L.tg_reduce_file(ctx.h, C.byref(capi.KVDesc(16, capi.OP_SUM_F64)), blocks, nb, C.byref(n_out)))
+    out = np.zeros(n_out.value, dtype=O.KV)
+    ob = (capi.Block * 1)(); ob[0].data = out.ctypes.data; ob[0].bytes = out.nbytes
+    ctx.ck(ctx.L.tg_fetch_output(ctx.h, ob, 1))
+    out = np.sort(out, order="key")
+    assert np.array_equal(out["key"], ref["key"])
+    a, b = out["val"].view(np.float64), ref["val"].view(np.float64)
+    assert np.all(np.abs(a - b) <= F64_RTOL * np.maximum(1.0, np.abs(b)))
+    # exact mode: bit-identical sums
+    ref = g["reduce_f64_exact_zipf_u4096_200000_w4"]
+    kv = O.gen_reduce_zipf(0, 200000, O.zipf_cdf(4096), exact=1)
+    out = _aggregate(ctx, kv, capi.OP_SUM_F64)
+    assert np.array_equal(out["key"], ref["key"]) and np.array_equal(out["val"], ref["val"])
+    ref = g["reduce_u64_uniform_u3000_100000_w2"]
+    kv = O.gen_reduce_uniform(0, 100000, universe=3000, exact=2)
+    out = _aggregate(ctx, kv, capi.OP_SUM_U64)
+    assert np.array_equal(out["key"], ref["key"]) and np.array_equal(out["val"], ref["val"])
+
+
+def test_reduce_large_device_generated_exact(ctx):
+    """5e7 Zipf records generated on the device, exact-mode values: every sum is bit-exact against the
+    oracle's straightforward aggregate, and the number of records is conserved (sum of counts)."""
+    from thrill_b200 import capi
+    n, U = 50000000, 1 << 22
+    cdf = O.zipf_cdf(U)
+    d_cdf = ctx.to_device(cdf)
+    d_in = ctx.alloc(n * 16)
+    ctx.ck(ctx.L.tg_gen_reduce_zipf(ctx.h, d_in, 0, n, 42, d_cdf, U, 1))
+    out_p = C.c_void_p(); out_n = C.c_size_t()
+    ctx.ck(ctx.L.tg_reduce_by_key(ctx.h, C.byref(capi.KVDesc(16, capi.OP_SUM_F64)), d_in, n, C.byref(out_p), C.byref(out_n)))
+    out = np.sort(ctx.download(out_p.value, out_n.value * 16, O.KV), order="key")
+    kv = O.gen_reduce_zipf(0, n, cdf, exact=1)
+    ref = O.reduce_simple(kv, O.OP_SUM_F64)
+    assert np.array_equal(out, ref)
+    ctx.free(d_in); ctx.free(d_cdf)

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "libthrill_gpu.so")
 TG_OK = 0
 KEY_UINT_LE, KEY_BYTES_BE = 0, 1
 OP_SUM_F64, OP_SUM_U64, OP_MIN_U64, OP_MAX_U64, OP_MIN_F64, OP_MAX_F64, OP_FIRST = range(7)
+K_RADIX_HIST, K_PARTITION, K_MERGE, K_PREAGG, K_AGGREGATE, K_COMPACT, K_OTHER = range(7)
 
 
 class KeyDesc(C.Structure):
@@ -63,6 +64,10 @@ SYMBOLS = [
     ("tg_timer_start", _i, [_vp]),
     ("tg_timer_stop", _i, [_vp, _P(C.c_float)]),
     ("tg_launch_count", _u64, [_vp]),
+    ("tg_profile_enable", _i, [_vp, _i]),
+    ("tg_profile_get", _i, [_vp, _i, _P(C.c_float), _P(_u64)]),
+    ("tg_host_alloc", _i, [_vp, _sz, _P(_vp)]),
+    ("tg_host_free", _i, [_vp, _vp]),
     ("tg_upload", _i, [_vp, _vp, _vp, _sz]),
     ("tg_download", _i, [_vp, _vp, _vp, _sz]),
     ("tg_upload_blocks", _i, [_vp, _vp, _P(Block), _sz, _P(_sz)]),
@@ -97,6 +102,22 @@ class ThrillGpuError(RuntimeError):
     pass
 
 
+def _preload_nccl():
+    """libthrill_gpu.so needs libnccl.so.2.  If PyTorch is (or will be) in the process, its bundled NCCL must
+    be the one the loader binds to that SONAME — an older system libnccl loaded first breaks `import torch`."""
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        spec = None
+    if spec and spec.submodule_search_locations:
+        for d in spec.submodule_search_locations:
+            cand = os.path.join(d, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                return
+
+
 def lib():
     """Load libthrill_gpu.so.  Raises if it has not been built: the product path never falls back."""
     global _lib
@@ -104,7 +125,8 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise ThrillGpuError("libthrill_gpu.so is not built (%s): run `python -c 'import __graft_entry__ as g; "
                                  "g.build()'` or `make -C thrill_b200/csrc`" % LIB_PATH)
-        L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        _preload_nccl()
+        L = C.CDLL(LIB_PATH)
         for name, res, args in SYMBOLS:
             fn = getattr(L, name)      # AttributeError if the library does not export a declared symbol
             fn.restype = res
@@ -191,6 +213,28 @@ class Ctx(object):
 
     def launches(self):
         return int(self.L.tg_launch_count(self.h))
+
+    def profile_enable(self, on=True):
+        self.ck(self.L.tg_profile_enable(self.h, int(on)))
+
+    def profile_get(self, cls):
+        ms = C.c_float(); cnt = C.c_uint64()
+        self.ck(self.L.tg_profile_get(self.h, cls, C.byref(ms), C.byref(cnt)))
+        return ms.value, cnt.value
+
+    def host_alloc(self, nbytes):
+        """page-locked host buffer as a numpy uint8 array (freed with host_free)"""
+        p = C.c_void_p()
+        self.ck(self.L.tg_host_alloc(self.h, max(nbytes, 16), C.byref(p)))
+        arr = self.np.ctypeslib.as_array((C.c_uint8 * max(nbytes, 16)).from_address(p.value))
+        arr = arr[:nbytes]
+        self._pinned = getattr(self, "_pinned", {})
+        self._pinned[arr.ctypes.data] = p.value
+        return arr
+
+    def host_free(self, arr):
+        p = self._pinned.pop(arr.ctypes.data)
+        self.ck(self.L.tg_host_free(self.h, p))
 
     # -- probes
     def checksum(self, dptr, n, item_bytes):

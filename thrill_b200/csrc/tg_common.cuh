@@ -30,6 +30,11 @@ struct tg_ctx {
     size_t ws_bytes[TG_NUM_WS] = { 0 };
     void* pinned = nullptr;                     // small pinned staging area (control-plane scalars)
     size_t pinned_bytes = 0;
+    // optional per-kernel-class timing (tg_profile_*)
+    bool profile = false;
+    struct ProfEv { int cls; cudaEvent_t a, b; };
+    std::vector<ProfEv> prof_events;
+    std::vector<cudaEvent_t> prof_pool;
     // result of the last *_file operator, fetched by tg_fetch_output
     void* out_ptr = nullptr;
     size_t out_items = 0;
@@ -65,10 +70,17 @@ int tg_ws_get(tg_ctx* ctx, int slot, size_t bytes, void** out);
         if (s_ != TG_OK) return s_;       \
     } while (0)
 
-// every kernel launch goes through this so tg_launch_count() is honest
-#define TG_LAUNCH(ctx, kernel, grid, block, smem, ...)                                             \
+int tg_prof_begin(tg_ctx* ctx, int cls);
+void tg_prof_end(tg_ctx* ctx, int slot);
+
+// every kernel launch goes through these so tg_launch_count() is honest; TG_LAUNCH_T also times the
+// launch with CUDA events when profiling is enabled
+#define TG_LAUNCH(ctx, kernel, grid, block, smem, ...) TG_LAUNCH_T(ctx, TG_K_OTHER, kernel, grid, block, smem, __VA_ARGS__)
+#define TG_LAUNCH_T(ctx, cls, kernel, grid, block, smem, ...)                                      \
     do {                                                                                           \
+        int ps_ = (ctx)->profile ? tg_prof_begin((ctx), (cls)) : -1;                               \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                           \
+        if (ps_ >= 0) tg_prof_end((ctx), ps_);                                                     \
         (ctx)->launches++;                                                                         \
         cudaError_t e_ = cudaGetLastError();                                                       \
         if (e_ != cudaSuccess)                                                                     \

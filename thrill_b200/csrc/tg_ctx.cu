@@ -37,7 +37,55 @@ int tg_ws_get(tg_ctx* ctx, int slot, size_t bytes, void** out) {
     return TG_OK;
 }
 
+int tg_prof_begin(tg_ctx* ctx, int cls) {
+    tg_ctx::ProfEv e;
+    e.cls = cls;
+    for (cudaEvent_t* ev : { &e.a, &e.b }) {
+        if (!ctx->prof_pool.empty()) { *ev = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); }
+        else if (cudaEventCreate(ev) != cudaSuccess) return -1;
+    }
+    cudaEventRecord(e.a, ctx->stream);
+    ctx->prof_events.push_back(e);
+    return (int)ctx->prof_events.size() - 1;
+}
+void tg_prof_end(tg_ctx* ctx, int slot) { cudaEventRecord(ctx->prof_events[slot].b, ctx->stream); }
+
 extern "C" {
+
+int tg_profile_enable(tg_ctx* ctx, int on) {
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto& e : ctx->prof_events) { ctx->prof_pool.push_back(e.a); ctx->prof_pool.push_back(e.b); }
+    ctx->prof_events.clear();
+    ctx->profile = on != 0;
+    return TG_OK;
+}
+
+int tg_profile_get(tg_ctx* ctx, int kernel_class, float* out_total_ms, uint64_t* out_launches) {
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float tot = 0.f;
+    uint64_t cnt = 0;
+    for (auto& e : ctx->prof_events)
+        if (e.cls == kernel_class) {
+            float ms = 0.f;
+            TG_CUDA(ctx, cudaEventElapsedTime(&ms, e.a, e.b));
+            tot += ms;
+            ++cnt;
+        }
+    if (out_total_ms) *out_total_ms = tot;
+    if (out_launches) *out_launches = cnt;
+    return TG_OK;
+}
+
+int tg_host_alloc(tg_ctx* ctx, size_t bytes, void** out_hptr) {
+    if (!out_hptr) return TG_ERR_ARG;
+    cudaError_t e = cudaMallocHost(out_hptr, bytes ? bytes : 16);
+    if (e != cudaSuccess) { cudaGetLastError(); return tg_set_error(ctx, TG_ERR_OOM, "cudaMallocHost(%zu) -> %s", bytes, cudaGetErrorString(e)); }
+    return TG_OK;
+}
+int tg_host_free(tg_ctx* ctx, void* hptr) {
+    if (hptr) TG_CUDA(ctx, cudaFreeHost(hptr));
+    return TG_OK;
+}
 
 int tg_version(void) { return 100; }
 
@@ -103,6 +151,8 @@ int tg_shutdown(tg_ctx* ctx) {
     for (int i = 0; i < TG_NUM_WS; ++i)
         if (ctx->ws[i]) cudaFree(ctx->ws[i]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (auto& e : ctx->prof_events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (auto& e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -39,6 +39,25 @@ struct RadixDigit {
     }
 };
 
+// warp-wide "which lanes hold the same 8-bit digit": 8 ballots + bit ops.  (match.any.sync costs ~64 issue
+// cycles of the ADU pipe per warp instruction on sm_100 — measured 66 % ADU-bound in profiles/ r1a — the
+// ballot form runs on the ordinary ALU/vote path.)
+template <bool CHECK_VALID>
+__device__ __forceinline__ u32 match_digit(u32 d, bool valid) {
+    u32 peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < RADIX_BITS; ++b) {
+        bool bit = (d >> b) & 1u;
+        u32 m = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? m : ~m;
+    }
+    if (CHECK_VALID) {
+        u32 m = __ballot_sync(0xffffffffu, valid);
+        peers &= valid ? m : ~m;
+    }
+    return peers;
+}
+
 template <int WORDS, int THREADS>
 struct SweepCfg {
     static constexpr int ITEM_BYTES = 8 * WORDS;
@@ -75,7 +94,7 @@ __global__ void __launch_bounds__(512) bucket_count_kernel(const typename ItemT<
 }
 
 // exclusive scan of npass digit histograms -> global bases; skip[p] = 1 if one bin holds everything
-__global__ void scan_hist_kernel(const u32* __restrict__ ghist, u32* __restrict__ gbase, u32* __restrict__ skip,
+static __global__ void scan_hist_kernel(const u32* __restrict__ ghist, u32* __restrict__ gbase, u32* __restrict__ skip,
                                  int npass, u32 n) {
     __shared__ u32 warp_tot[RADIX / 32];
     const int d = threadIdx.x;      // RADIX threads
@@ -173,25 +192,44 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
         }
         __syncwarp();
 
-        // ---- stable rank inside the warp: match.any groups equal digits, the group leader bumps the counter
+        // ---- stable rank inside the warp: ballots group equal digits, the group leader bumps the counter
         unsigned short rank[ITEMS];
         unsigned char mydig[ITEMS];
+        if (full_tile) {
 #pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-            u32 p = wbase + i * 32 + lane;
-            bool valid = p < tile_valid;
-            u32 d = valid ? fn(key[i], tile_base + p) : (u32)(RADIX + lane);
-            mydig[i] = (unsigned char)d;
-            u32 peers = __match_any_sync(0xffffffffu, d);
-            int leader = __ffs(peers) - 1;
-            u32 old = 0;
-            if (lane == leader && valid) {
-                old = whist[warp * RADIX + d];
-                whist[warp * RADIX + d] = old + __popc(peers);
+            for (int i = 0; i < ITEMS; ++i) {
+                u32 d = fn(key[i], tile_base + wbase + i * 32 + lane);
+                mydig[i] = (unsigned char)d;
+                u32 peers = match_digit<false>(d, true);
+                int leader = __ffs(peers) - 1;
+                u32 old = 0;
+                if (lane == leader) {
+                    old = whist[warp * RADIX + d];
+                    whist[warp * RADIX + d] = old + __popc(peers);
+                }
+                old = __shfl_sync(0xffffffffu, old, leader);
+                rank[i] = (unsigned short)(old + __popc(peers & lt));
+                __syncwarp();
             }
-            old = __shfl_sync(0xffffffffu, old, leader);
-            rank[i] = (unsigned short)(old + __popc(peers & lt));
-            __syncwarp();
+        }
+        else {
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) {
+                u32 p = wbase + i * 32 + lane;
+                bool valid = p < tile_valid;
+                u32 d = valid ? fn(key[i], tile_base + p) : 0u;
+                mydig[i] = (unsigned char)d;
+                u32 peers = match_digit<true>(d, valid);
+                int leader = __ffs(peers) - 1;
+                u32 old = 0;
+                if (lane == leader && valid) {
+                    old = whist[warp * RADIX + d];
+                    whist[warp * RADIX + d] = old + __popc(peers);
+                }
+                old = __shfl_sync(0xffffffffu, old, leader);
+                rank[i] = (unsigned short)(old + __popc(peers & lt));
+                __syncwarp();
+            }
         }
         __syncthreads();      // all items are in registers (buf is free), all warp counters final
 
@@ -299,7 +337,7 @@ int launch_partition(tg_ctx* ctx, const void* in, void* out, u32 n, const DigitF
     }
     u32 num_tiles = (n + C::TILE - 1) / C::TILE;
     int grid = ctx->sm_count < (int)num_tiles ? ctx->sm_count : (int)num_tiles;
-    TG_LAUNCH(ctx, kern, grid, SWEEP_THREADS, C::SMEM, (const Item*)in, (Item*)out, n, fn, gbase, status);
+    TG_LAUNCH_T(ctx, TG_K_PARTITION, kern, grid, SWEEP_THREADS, C::SMEM, (const Item*)in, (Item*)out, n, fn, gbase, status);
     return TG_OK;
 }
 

@@ -83,7 +83,7 @@ int radix_sort_impl(tg_ctx* ctx, const PassList& pl, void* d_items, void* d_tmp,
     TG_CUDA(ctx, cudaMemsetAsync(hist, 0, hist_words * 4, ctx->stream));
     TG_CUDA(ctx, cudaMemsetAsync(status, 0, status_bytes, ctx->stream));
 
-    TG_LAUNCH(ctx, radix_hist_kernel<WORDS>, ctx->sm_count * 2, 512, pl.npass * RADIX * 4, (const Item*)d_items, n, pl, hist);
+    TG_LAUNCH_T(ctx, TG_K_RADIX_HIST, radix_hist_kernel<WORDS>, ctx->sm_count * 2, 512, pl.npass * RADIX * 4, (const Item*)d_items, n, pl, hist);
     TG_LAUNCH(ctx, scan_hist_kernel, 1, RADIX, 0, hist, gbase, skip, pl.npass, (u32)n);
     u32* h_skip = (u32*)ctx->pinned;
     TG_CUDA(ctx, cudaMemcpyAsync(h_skip, skip, pl.npass * 4, cudaMemcpyDeviceToHost, ctx->stream));

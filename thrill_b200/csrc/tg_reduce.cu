@@ -1,0 +1,376 @@
+// tg_reduce.cu — the hash-aggregate operator of Thrill's ReduceNode (ReduceByKey / ReducePair) on B200s.
+//
+// Reference path replaced: ReducePrePhase::Insert -> ReduceProbingHashTable::Insert (open addressing,
+// linear probing, Key()==0 sentinel in a side slot; core/reduce_probing_hash_table.hpp:190-268), FlushAll
+// -> ReducePrePhaseEmitter::Emit into the writer of worker Hash128to64(0,key) % p
+// (core/reduce_pre_phase.hpp:57-61, core/reduce_functional.hpp:60-72), the MixStream exchange
+// (api/reduce_by_key.hpp:109-114), and ReduceByHashPostPhase (core/reduce_by_hash_post_phase.hpp:44-281).
+//
+// GPU formulation (same result set; output order is table order = unspecified in the reference too):
+//   pre phase   : per-CTA shared-memory probing tables absorb the head of the key distribution (the Zipf
+//                 hot keys never reach global atomics); tables are flushed as partial aggregates
+//   partition   : stable 256-way partition kernel with digit = Hash128to64(0,key) % p   (p > 1 only)
+//   exchange    : NCCL Alltoallv of the p contiguous groups                             (p > 1 only)
+//   post phase  : open-addressing table in HBM (16-byte slots, atomicCAS on the key, native atomics on the
+//                 value), sized from the number of partial aggregates, then compaction of the used slots
+#include "tg_partition.cuh"
+
+using namespace tgp;
+
+namespace {
+
+// ---- the reduce functions the host shim recognises -----------------------------------------------------------
+__device__ __forceinline__ u64 op_identity(int op) {
+    switch (op) {
+    case TG_OP_MIN_U64: return ~0ull;
+    case TG_OP_MIN_F64: return 0x7FF0000000000000ull;      // +inf
+    case TG_OP_MAX_F64: return 0xFFF0000000000000ull;      // -inf
+    default: return 0ull;                                  // sums, max_u64, first
+    }
+}
+__host__ inline bool op_identity_is_zero(int op) {
+    return op == TG_OP_SUM_F64 || op == TG_OP_SUM_U64 || op == TG_OP_MAX_U64 || op == TG_OP_FIRST;
+}
+
+// atomically fold `val` into *slot_val; `claimed` = this thread created the slot (needed for FIRST)
+__device__ __forceinline__ void op_apply(int op, u64* slot_val, u64 val, bool claimed) {
+    switch (op) {
+    case TG_OP_SUM_F64: atomicAdd((double*)slot_val, __longlong_as_double((long long)val)); break;
+    case TG_OP_SUM_U64: atomicAdd(slot_val, val); break;
+    case TG_OP_MIN_U64: atomicMin(slot_val, val); break;
+    case TG_OP_MAX_U64: atomicMax(slot_val, val); break;
+    case TG_OP_MIN_F64:
+    case TG_OP_MAX_F64: {
+        double v = __longlong_as_double((long long)val);
+        u64 old = *(volatile u64*)slot_val;
+        while (true) {
+            double o = __longlong_as_double((long long)old);
+            bool better = (op == TG_OP_MIN_F64) ? (v < o) : (o < v);
+            if (!better) break;
+            u64 prev = atomicCAS(slot_val, old, val);
+            if (prev == old) break;
+            old = prev;
+        }
+        break;
+    }
+    default:      // TG_OP_FIRST: the value that created the slot stays
+        if (claimed) atomicExch(slot_val, val);
+        break;
+    }
+}
+
+__device__ __forceinline__ u64 key_hash(u64 key) { return hash128to64_dev(0, key); }
+
+// ---- pre phase: per-CTA shared-memory tables ----------------------------------------------------------------------
+constexpr int PRE_THREADS = 1024;
+constexpr int PRE_SLOTS = 8192;                  // 64 KB keys + 64 KB values
+constexpr int PRE_MAXPROBE = 8;
+constexpr int PRE_CHUNK = PRE_THREADS * 4;       // records between fill checks
+constexpr int PRE_SMEM = PRE_SLOTS * 16 + 64;
+
+// append one item to the global output (warp-aggregated cursor bump)
+__device__ __forceinline__ void emit_item(ulonglong2* __restrict__ out, u64* cursor, u64 key, u64 val, bool has) {
+    u32 m = __ballot_sync(0xffffffffu, has);
+    if (!m) return;
+    u64 base = 0;
+    int leader = __ffs(m) - 1;
+    if ((int)lane_id() == leader) base = atomicAdd(cursor, (u64)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (has) out[base + __popc(m & lanemask_lt())] = make_ulonglong2(key, val);
+}
+
+__global__ void __launch_bounds__(PRE_THREADS, 1)
+preagg_kernel(const ulonglong2* __restrict__ in, u64 n, int op, ulonglong2* __restrict__ out, u64* __restrict__ cursor,
+              u64* __restrict__ zero_slot /* [0]=flag, [1]=value */) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    u64* keys = (u64*)smem;
+    u64* vals = keys + PRE_SLOTS;
+    u32* fill = (u32*)(vals + PRE_SLOTS);
+    const u64 ident = op_identity(op);
+    for (int i = threadIdx.x; i < PRE_SLOTS; i += PRE_THREADS) { keys[i] = 0; vals[i] = ident; }
+    if (threadIdx.x == 0) *fill = 0;
+    __syncthreads();
+
+    const u64 per_cta = (n + gridDim.x - 1) / gridDim.x;
+    const u64 lo = per_cta * blockIdx.x;
+    const u64 hi = lo + per_cta < n ? lo + per_cta : n;
+    for (u64 base = lo; base < hi; base += PRE_CHUNK) {
+#pragma unroll
+        for (int j = 0; j < PRE_CHUNK / PRE_THREADS; ++j) {
+            u64 i = base + (u64)j * PRE_THREADS + threadIdx.x;
+            bool valid = i < hi;
+            ulonglong2 kv = valid ? in[i] : make_ulonglong2(0, 0);
+            bool spill = false;
+            if (valid) {
+                if (kv.x == 0) {
+                    // Key() == 0: reduced in a side slot, never probed (reduce_probing_hash_table.hpp:195-218)
+                    u64 prev = atomicCAS(&zero_slot[0], 0ull, 1ull);
+                    op_apply(op, &zero_slot[1], kv.y, prev == 0);
+                }
+                else {
+                    u32 slot = (u32)(key_hash(kv.x) >> 32) & (PRE_SLOTS - 1);
+                    spill = true;
+#pragma unroll 1
+                    for (int pr = 0; pr < PRE_MAXPROBE; ++pr) {
+                        u64 prev = atomicCAS(&keys[slot], 0ull, kv.x);
+                        if (prev == 0 || prev == kv.x) {
+                            if (prev == 0) atomicAdd(fill, 1u);
+                            op_apply(op, &vals[slot], kv.y, prev == 0);
+                            spill = false;
+                            break;
+                        }
+                        slot = (slot + 1) & (PRE_SLOTS - 1);
+                    }
+                }
+            }
+            // probe limit hit: pass the record through unreduced (a legal partial aggregate)
+            emit_item(out, cursor, kv.x, kv.y, spill);
+        }
+        __syncthreads();
+        const bool last = base + PRE_CHUNK >= hi;
+        if (*fill > PRE_SLOTS * 3 / 4 || last) {
+            // FlushPartition (reduce_probing_hash_table.hpp:443-482): emit every used slot, reset the table
+            for (int i = threadIdx.x; i < PRE_SLOTS; i += PRE_THREADS) {
+                u64 k = keys[i];
+                emit_item(out, cursor, k, vals[i], k != 0);
+                keys[i] = 0; vals[i] = ident;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) *fill = 0;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- post phase: open addressing in HBM ------------------------------------------------------------------------
+__global__ void table_init_kernel(ulonglong2* __restrict__ tab, u64 cap, u64 ident) {
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += stride) tab[i] = make_ulonglong2(0, ident);
+}
+
+__global__ void __launch_bounds__(512)
+aggregate_kernel(const ulonglong2* __restrict__ in, u64 n, int op, ulonglong2* __restrict__ tab, u64 cap,
+                 u64* __restrict__ zero_slot) {
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        ulonglong2 kv = in[i];
+        if (kv.x == 0) {
+            u64 prev = atomicCAS(&zero_slot[0], 0ull, 1ull);
+            op_apply(op, &zero_slot[1], kv.y, prev == 0);
+            continue;
+        }
+        u64 slot = __umul64hi(key_hash(kv.x), cap);       // uniform hash -> [0, cap)
+        while (true) {
+            u64* kp = &tab[slot].x;
+            u64 prev = *(volatile u64*)kp;
+            if (prev == 0) prev = atomicCAS(kp, 0ull, kv.x);
+            if (prev == 0 || prev == kv.x) {
+                op_apply(op, &tab[slot].y, kv.y, prev == 0);
+                break;
+            }
+            if (++slot == cap) slot = 0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(512)
+compact_kernel(const ulonglong2* __restrict__ tab, u64 cap, ulonglong2* __restrict__ out, u64* __restrict__ cursor,
+               const u64* __restrict__ zero_slot) {
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    u64 rounds = (cap + stride - 1) / stride;
+    for (u64 r = 0; r < rounds; ++r) {
+        u64 i = r * stride + (u64)blockIdx.x * blockDim.x + threadIdx.x;
+        ulonglong2 e = i < cap ? tab[i] : make_ulonglong2(0, 0);
+        emit_item(out, cursor, e.x, e.y, e.x != 0);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 32) emit_item(out, cursor, 0ull, zero_slot[1], threadIdx.x == 0 && zero_slot[0] != 0);
+}
+
+// destination worker of an item: Hash128to64(0, key) % p  (core/reduce_functional.hpp:60-72)
+struct HashDigit {
+    u32 p;
+    static constexpr bool kStoreDigit = true;
+    __device__ __forceinline__ u32 operator()(const ulonglong2& v, u32) const { return (u32)(key_hash(v.x) % p); }
+    __device__ __forceinline__ u32 operator()(const u64& v, u32) const { return (u32)(key_hash(v) % p); }
+};
+
+struct ReduceScratch {
+    u64* cursor;        // [0] output cursor
+    u64* zero_slot;     // [0] flag, [1] value
+};
+
+int get_scratch(tg_ctx* ctx, int op, ReduceScratch* sc) {
+    u64* d;
+    TG_TRY(tg_ws_get(ctx, WS_MISC, 1 << 16, (void**)&d));
+    sc->cursor = d + 4096;
+    sc->zero_slot = d + 4100;
+    u64 init[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    u64 ident = (op == TG_OP_MIN_U64) ? ~0ull : (op == TG_OP_MIN_F64) ? 0x7FF0000000000000ull
+              : (op == TG_OP_MAX_F64) ? 0xFFF0000000000000ull : 0ull;
+    init[5] = ident;        // zero_slot[1]
+    u64* h = (u64*)ctx->pinned + 1024;
+    memcpy(h, init, sizeof(init));
+    TG_CUDA(ctx, cudaMemcpyAsync(sc->cursor, h, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    return TG_OK;
+}
+
+int read_cursor(tg_ctx* ctx, const ReduceScratch& sc, u64* out) {
+    u64* h = (u64*)ctx->pinned + 2048;
+    TG_CUDA(ctx, cudaMemcpyAsync(h, sc.cursor, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = h[0];
+    return TG_OK;
+}
+
+// pre phase: n records -> m partial aggregates in d_pre (capacity n + 1)
+int run_preagg(tg_ctx* ctx, int op, const void* d_in, u64 n, void* d_pre, u64* out_m) {
+    ReduceScratch sc;
+    TG_TRY(get_scratch(ctx, op, &sc));
+    static bool attr_set = false;
+    if (!attr_set) {
+        TG_CUDA(ctx, cudaFuncSetAttribute(preagg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PRE_SMEM));
+        attr_set = true;
+    }
+    if (n) {
+        u64 ctas = (n + PRE_CHUNK - 1) / PRE_CHUNK;
+        int grid = ctas < (u64)ctx->sm_count ? (int)ctas : ctx->sm_count;
+        TG_LAUNCH_T(ctx, TG_K_PREAGG, preagg_kernel, grid, PRE_THREADS, PRE_SMEM, (const ulonglong2*)d_in, n, op, (ulonglong2*)d_pre, sc.cursor, sc.zero_slot);
+    }
+    // the zero key's partial aggregate travels as one more item
+    TG_LAUNCH(ctx, compact_kernel, 1, 32, 0, (const ulonglong2*)nullptr, (u64)0, (ulonglong2*)d_pre, sc.cursor, sc.zero_slot);
+    return read_cursor(ctx, sc, out_m);
+}
+
+// post phase: m (partial) items -> distinct keys in d_out (capacity m)
+int run_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 m, void* d_out, u64* out_distinct) {
+    ReduceScratch sc;
+    TG_TRY(get_scratch(ctx, op, &sc));
+    if (m == 0) { *out_distinct = 0; return TG_OK; }
+    u64 cap = m + m / 2 + 64;                     // load factor <= 2/3
+    ulonglong2* tab;
+    TG_TRY(tg_ws_get(ctx, WS_TABLE, cap * 16, (void**)&tab));
+    if (op_identity_is_zero(op)) TG_CUDA(ctx, cudaMemsetAsync(tab, 0, cap * 16, ctx->stream));
+    else {
+        u64 ident = (op == TG_OP_MIN_U64) ? ~0ull : (op == TG_OP_MIN_F64) ? 0x7FF0000000000000ull : 0xFFF0000000000000ull;
+        TG_LAUNCH(ctx, table_init_kernel, ctx->sm_count * 8, 512, 0, tab, cap, ident);
+    }
+    TG_LAUNCH_T(ctx, TG_K_AGGREGATE, aggregate_kernel, ctx->sm_count * 4, 512, 0, (const ulonglong2*)d_in, m, op, tab, cap, sc.zero_slot);
+    TG_LAUNCH_T(ctx, TG_K_COMPACT, compact_kernel, ctx->sm_count * 4, 512, 0, (const ulonglong2*)tab, cap, (ulonglong2*)d_out, sc.cursor, sc.zero_slot);
+    return read_cursor(ctx, sc, out_distinct);
+}
+
+int check_kv(tg_ctx* ctx, const tg_kv_desc* d) {
+    if (!ctx || !d || d->item_bytes != 16 || d->op > TG_OP_FIRST)
+        return tg_set_error(ctx, TG_ERR_ARG, "reduce: only 16-byte (u64 key, 8-byte value) items and TG_OP_* are supported");
+    return TG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tg_hash_aggregate(tg_ctx* ctx, const tg_kv_desc* desc, const void* d_in, size_t n, void* d_out, uint64_t* out_distinct) {
+    TG_TRY(check_kv(ctx, desc));
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    // pre phase into scratch, post phase into d_out
+    void* d_pre;
+    TG_TRY(tg_ws_get(ctx, WS_AUX, (n + 2) * 16, &d_pre));
+    u64 m = 0;
+    TG_TRY(run_preagg(ctx, (int)desc->op, d_in, n, d_pre, &m));
+    u64 distinct = 0;
+    TG_TRY(run_aggregate(ctx, (int)desc->op, d_pre, m, d_out, &distinct));
+    *out_distinct = distinct;
+    return TG_OK;
+}
+
+int tg_hash_partition(tg_ctx* ctx, const tg_kv_desc* desc, const void* d_in, size_t n, uint32_t p, void* d_out, uint64_t* out_counts) {
+    TG_TRY(check_kv(ctx, desc));
+    if (p == 0 || p > RADIX) return tg_set_error(ctx, TG_ERR_ARG, "hash_partition: p=%u", p);
+    if (n >= (1u << 30)) return tg_set_error(ctx, TG_ERR_TOO_LARGE, "hash_partition: n=%zu", n);
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    HashDigit fn = { p };
+    u32* d_counts = nullptr;
+    TG_TRY((partition_items<2, HashDigit>(ctx, d_in, d_out, (u32)n, fn, &d_counts)));
+    u32* hc = (u32*)ctx->pinned;
+    TG_CUDA(ctx, cudaMemcpyAsync(hc, d_counts, RADIX * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (uint32_t r = 0; r < p; ++r) out_counts[r] = hc[r];
+    return TG_OK;
+}
+
+int tg_reduce_by_key(tg_ctx* ctx, const tg_kv_desc* desc, const void* d_in, size_t n_local, void** out_dptr, size_t* out_n) {
+    TG_TRY(check_kv(ctx, desc));
+    if (!out_dptr || !out_n) return TG_ERR_ARG;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int op = (int)desc->op;
+    const int p = ctx->nranks, me = ctx->rank;
+    // pre phase (ReducePrePhase, StartPreOp..StopPreOp: api/reduce_by_key.hpp:142-168)
+    void* d_pre;
+    TG_TRY(tg_ws_get(ctx, WS_AUX, (n_local + 2) * 16, &d_pre));
+    u64 m = 0;
+    TG_TRY(run_preagg(ctx, op, d_in, n_local, d_pre, &m));
+    const void* d_post_in = d_pre;
+    u64 m_post = m;
+    if (p > 1) {
+        if (m >= (1u << 30)) return tg_set_error(ctx, TG_ERR_TOO_LARGE, "reduce: %llu partial aggregates", m);
+        // partition by Hash128to64(0,key) % p, exchange (replaces the MixStream writers, :109-114)
+        void* d_send;
+        TG_TRY(tg_ws_get(ctx, WS_XCHG_SEND, (m + 2) * 16, &d_send));
+        HashDigit fn = { (u32)p };
+        u32* d_counts = nullptr;
+        TG_TRY((partition_items<2, HashDigit>(ctx, d_pre, d_send, (u32)m, fn, &d_counts)));
+        u32* hc = (u32*)ctx->pinned;
+        TG_CUDA(ctx, cudaMemcpyAsync(hc, d_counts, RADIX * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        std::vector<u64> send_cnt(p), send_off(p + 1, 0);
+        for (int r = 0; r < p; ++r) { send_cnt[r] = hc[r]; send_off[r + 1] = send_off[r] + send_cnt[r]; }
+        u64* h = (u64*)ctx->pinned;
+        u64* d_ctl;
+        TG_TRY(tg_ws_get(ctx, WS_MISC, 1 << 16, (void**)&d_ctl));
+        for (int r = 0; r < p; ++r) h[r] = send_cnt[r];
+        TG_CUDA(ctx, cudaMemcpyAsync(d_ctl, h, 8 * p, cudaMemcpyHostToDevice, ctx->stream));
+        TG_NCCL(ctx, ncclAllGather(d_ctl, d_ctl + 64, p, ncclUint64, ctx->comm, ctx->stream));
+        TG_CUDA(ctx, cudaMemcpyAsync(h, d_ctl + 64, 8 * p * p, cudaMemcpyDeviceToHost, ctx->stream));
+        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        std::vector<u64> recv_cnt(p), recv_off(p + 1, 0);
+        for (int r = 0; r < p; ++r) { recv_cnt[r] = h[(size_t)r * p + me]; recv_off[r + 1] = recv_off[r] + recv_cnt[r]; }
+        ulonglong2* d_recv;
+        TG_TRY(tg_ws_get(ctx, WS_XCHG_RECV, (recv_off[p] + 2) * 16, (void**)&d_recv));
+        TG_NCCL(ctx, ncclGroupStart());
+        for (int r = 0; r < p; ++r) {
+            if (send_cnt[r]) TG_NCCL(ctx, ncclSend((const ulonglong2*)d_send + send_off[r], send_cnt[r] * 16, ncclUint8, r, ctx->comm, ctx->stream));
+            if (recv_cnt[r]) TG_NCCL(ctx, ncclRecv(d_recv + recv_off[r], recv_cnt[r] * 16, ncclUint8, r, ctx->comm, ctx->stream));
+        }
+        TG_NCCL(ctx, ncclGroupEnd());
+        d_post_in = d_recv;
+        m_post = recv_off[p];
+    }
+    // post phase (ReduceByHashPostPhase, ProcessChannel + PushData: api/reduce_by_key.hpp:176-211)
+    void* d_out;
+    TG_TRY(tg_ws_get(ctx, WS_OUT, (m_post + 2) * 16, &d_out));
+    u64 distinct = 0;
+    TG_TRY(run_aggregate(ctx, op, d_post_in, m_post, d_out, &distinct));
+    *out_dptr = d_out;
+    *out_n = (size_t)distinct;
+    return TG_OK;
+}
+
+int tg_reduce_file(tg_ctx* ctx, const tg_kv_desc* desc, const tg_block* in_blocks, size_t n_in_blocks, size_t* out_items) {
+    TG_TRY(check_kv(ctx, desc));
+    if (!out_items) return TG_ERR_ARG;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t bytes = 0;
+    for (size_t i = 0; i < n_in_blocks; ++i) bytes += in_blocks[i].bytes;
+    if (bytes % 16) return tg_set_error(ctx, TG_ERR_ARG, "reduce_file: %zu bytes is not a multiple of 16", bytes);
+    void* d_in;
+    TG_TRY(tg_ws_get(ctx, WS_IN, bytes + 16, &d_in));
+    TG_TRY(tg_upload_blocks(ctx, d_in, in_blocks, n_in_blocks, nullptr));
+    void* out = nullptr;
+    size_t n_out = 0;
+    TG_TRY(tg_reduce_by_key(ctx, desc, d_in, bytes / 16, &out, &n_out));
+    ctx->out_ptr = out; ctx->out_items = n_out; ctx->out_item_bytes = 16;
+    *out_items = n_out;
+    return TG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,554 @@
+// tg_sample_sort.cu — the sample-sort operator of Thrill's SortNode on B200s (one GPU per worker).
+//
+// Reference path replaced (api/sort.hpp): OnPreOpFile sampling (:151-175), MainOp (:537-663) =
+// ExPrefixSumTotal (:541), samples -> FindAndSendSplitters (:337-378), TreeBuilder + TransmitItems
+// classification with the global-index tie-break (:380-426, :434-535), the MixStream exchange (:615-641),
+// ReceiveItems/SortAndWriteToFile local sort (:665-742) and the multiway merge of PushData (:216-271,
+// core/multiway_merge.hpp:30-116).
+//
+// GPU formulation (the "sorted runs" form named in the north star; same output contract):
+//   local LSB radix sort -> splitter bucket boundaries (classification of a sorted, stable shard is a
+//   set of p-1 positions: lower_bound by key + the number of equal-key items with global index <= the
+//   splitter's index) -> NCCL Alltoallv of the p contiguous ranges -> k-way merge of the p received runs.
+// The stand-alone classify+scatter kernel (tg_classify_scatter, for unsorted input, the literal
+// TransmitItems) and the k-way merge kernel are exported for parity tests and ncu captures.
+#include <algorithm>
+#include <cmath>
+
+#include "tg_partition.cuh"
+
+using namespace tgp;
+
+int tg_radix_sort_items(tg_ctx* ctx, const tg_key_desc* desc, void* d_items, void* d_tmp, size_t n);
+
+namespace {
+
+// ---- canonical keys: (hi, lo) compared as unsigned 128-bit == the reference comparator's order ----------
+struct KeyView {
+    u32 off, bytes, kind, desc;
+};
+
+struct Canon {
+    u64 hi, lo;
+};
+struct CanonIdx {
+    u64 hi, lo, idx;
+};
+
+__host__ __device__ inline bool canon_less(const Canon& a, const Canon& b) {
+    return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo);
+}
+__host__ __device__ inline bool canon_eq(const Canon& a, const Canon& b) { return a.hi == b.hi && a.lo == b.lo; }
+// LessSampleIndex (api/sort.hpp:419-422) on canonical keys
+__host__ __device__ inline bool canonidx_less(const CanonIdx& a, const CanonIdx& b) {
+    if (a.hi != b.hi) return a.hi < b.hi;
+    if (a.lo != b.lo) return a.lo < b.lo;
+    return a.idx < b.idx;
+}
+
+// byte j of an item held as little-endian u64 words
+template <class Item>
+__device__ __forceinline__ u32 item_byte(const Item& v, u32 j) {
+    return (u32)(item_word(v, (int)(j >> 3)) >> (8 * (j & 7))) & 0xffu;
+}
+
+template <class Item>
+__device__ __forceinline__ Canon canon_key(const Item& v, const KeyView& kv) {
+    Canon c;
+    c.hi = 0; c.lo = 0;
+    if (kv.kind == TG_KEY_UINT_LE) {
+        if (kv.bytes == 8 && (kv.off & 7) == 0) c.lo = item_word(v, (int)(kv.off >> 3));
+        else
+            for (u32 j = 0; j < kv.bytes; ++j) c.lo |= (u64)item_byte(v, kv.off + j) << (8 * j);
+    }
+    else {
+        for (u32 j = 0; j < kv.bytes && j < 8; ++j) c.hi |= (u64)item_byte(v, kv.off + j) << (8 * (7 - j));
+        for (u32 j = 8; j < kv.bytes; ++j) c.lo |= (u64)item_byte(v, kv.off + j) << (8 * (15 - j));
+    }
+    if (kv.desc) { c.hi = ~c.hi; c.lo = ~c.lo; }
+    return c;
+}
+
+Canon canon_key_host(const unsigned char* item, const KeyView& kv) {
+    Canon c;
+    c.hi = 0; c.lo = 0;
+    if (kv.kind == TG_KEY_UINT_LE) {
+        for (u32 j = 0; j < kv.bytes; ++j) c.lo |= (u64)item[kv.off + j] << (8 * j);
+    }
+    else {
+        for (u32 j = 0; j < kv.bytes && j < 8; ++j) c.hi |= (u64)item[kv.off + j] << (8 * (7 - j));
+        for (u32 j = 8; j < kv.bytes; ++j) c.lo |= (u64)item[kv.off + j] << (8 * (15 - j));
+    }
+    if (kv.desc) { c.hi = ~c.hi; c.lo = ~c.lo; }
+    return c;
+}
+
+int make_key_view(const tg_key_desc* d, KeyView* kv) {
+    if (!d) return TG_ERR_ARG;
+    if (d->key_bytes == 0 || d->key_offset + d->key_bytes > d->item_bytes) return TG_ERR_ARG;
+    if (d->key_kind == TG_KEY_UINT_LE && d->key_bytes > 8) return TG_ERR_ARG;
+    if (d->key_kind == TG_KEY_BYTES_BE && d->key_bytes > 16) return TG_ERR_ARG;
+    if (d->key_kind != TG_KEY_UINT_LE && d->key_kind != TG_KEY_BYTES_BE) return TG_ERR_ARG;
+    kv->off = d->key_offset; kv->bytes = d->key_bytes; kv->kind = d->key_kind; kv->desc = d->descending;
+    return TG_OK;
+}
+
+// ---- classification by splitters: bucket = #splitters (key, idx) < (item key, item global index) ----
+// == TransmitItems' tree descent + EqualSampleGreaterIndex walk (api/sort.hpp:478-502); the padded
+// sentinel splitters (:607-609) and the writer swap (:460) only exist to make the tree a power of two.
+struct SplitterDigit {
+    const CanonIdx* spl;
+    u32 nspl;
+    u64 gbase;
+    KeyView kv;
+    static constexpr bool kStoreDigit = true;
+    template <class Item>
+    __device__ __forceinline__ u32 operator()(const Item& v, u32 pos) const {
+        Canon k = canon_key(v, kv);
+        CanonIdx me = { k.hi, k.lo, gbase + pos };
+        u32 lo = 0, hi = nspl;
+        while (lo < hi) {
+            u32 mid = (lo + hi) >> 1;
+            CanonIdx s = spl[mid];
+            if (canonidx_less(s, me)) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    }
+};
+
+// ---- sampling: gather items at pseudo-random positions (OnPreOpFile, api/sort.hpp:162-170) --------------
+template <int WORDS>
+__global__ void draw_samples_kernel(const typename ItemT<WORDS>::type* __restrict__ in, u64 n, u64 gbase, u64 seed,
+                                    u32 nsamples, KeyView kv, typename ItemT<WORDS>::type* __restrict__ out_items,
+                                    CanonIdx* __restrict__ out_canon) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nsamples) return;
+    u64 index = splitmix64_dev(seed + i) % n;
+    typename ItemT<WORDS>::type v = in[index];
+    if (out_items) out_items[i] = v;
+    Canon c = canon_key(v, kv);
+    CanonIdx ci = { c.hi, c.lo, gbase + index };
+    out_canon[i] = ci;
+}
+
+// ---- number of local items equal to splitter j's key with global index <= splitter j's index ------------
+template <int WORDS>
+__global__ void tie_count_kernel(const typename ItemT<WORDS>::type* __restrict__ in, u32 n, u64 gbase, KeyView kv,
+                                 const CanonIdx* __restrict__ spl, u32 nspl, u32* __restrict__ tie) {
+    u32 stride = gridDim.x * blockDim.x;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        Canon k = canon_key(in[i], kv);
+        u32 lo = 0, hi = nspl;
+        while (lo < hi) {           // first splitter with key >= k
+            u32 mid = (lo + hi) >> 1;
+            Canon s = { spl[mid].hi, spl[mid].lo };
+            if (canon_less(s, k)) lo = mid + 1; else hi = mid;
+        }
+        while (lo < nspl) {
+            CanonIdx s = spl[lo];
+            Canon sk = { s.hi, s.lo };
+            if (!canon_eq(sk, k)) break;
+            if (gbase + i <= s.idx) atomicAdd(&tie[lo], 1u);
+            ++lo;
+        }
+    }
+}
+
+// bnd[j] = lower_bound(sorted, splitter j key) + tie[j]   (one thread per splitter)
+template <int WORDS>
+__global__ void boundaries_kernel(const typename ItemT<WORDS>::type* __restrict__ sorted, u32 n, KeyView kv,
+                                  const CanonIdx* __restrict__ spl, u32 nspl, const u32* __restrict__ tie,
+                                  u64* __restrict__ bnd) {
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nspl) return;
+    Canon s = { spl[j].hi, spl[j].lo };
+    u32 lo = 0, hi = n;
+    while (lo < hi) {
+        u32 mid = lo + ((hi - lo) >> 1);
+        if (canon_less(canon_key(sorted[mid], kv), s)) lo = mid + 1; else hi = mid;
+    }
+    bnd[j] = (u64)lo + tie[j];
+}
+
+// ---- 2-way merge (merge path), stable: ties take from A (the run with the lower index) --------------------
+constexpr int MG_THREADS = 256;
+template <int WORDS> struct MergeCfg { static constexpr int VT = 16 / WORDS; static constexpr int TILE = MG_THREADS * VT; };
+
+template <int WORDS, class Item>
+__device__ __forceinline__ u32 merge_path_search(const Item* A, u32 na, const Item* B, u32 nb, u32 diag, const KeyView& kv) {
+    // number of A items among the first `diag` merged outputs
+    u32 lo = diag > nb ? diag - nb : 0, hi = diag < na ? diag : na;
+    while (lo < hi) {
+        u32 mid = (lo + hi) >> 1;            // take mid+1 items from A?
+        Canon a = canon_key(A[mid], kv);
+        Canon b = canon_key(B[diag - 1 - mid], kv);
+        if (canon_less(b, a)) hi = mid; else lo = mid + 1;      // A[mid] <= B[..] -> A first (stable)
+    }
+    return lo;
+}
+
+template <int WORDS>
+__global__ void __launch_bounds__(MG_THREADS)
+merge2_kernel(const typename ItemT<WORDS>::type* __restrict__ A, u32 na, const typename ItemT<WORDS>::type* __restrict__ B,
+              u32 nb, typename ItemT<WORDS>::type* __restrict__ out, KeyView kv) {
+    typedef typename ItemT<WORDS>::type Item;
+    constexpr int VT = MergeCfg<WORDS>::VT, TILE = MergeCfg<WORDS>::TILE;
+    __shared__ Item sm[TILE + 1];
+    __shared__ u32 split[2];
+    const u32 total = na + nb;
+    const u32 o0 = blockIdx.x * TILE;
+    const u32 o1 = o0 + TILE < total ? o0 + TILE : total;
+    if (threadIdx.x < 2) split[threadIdx.x] = merge_path_search<WORDS>(A, na, B, nb, threadIdx.x ? o1 : o0, kv);
+    __syncthreads();
+    const u32 a0 = split[0], a1 = split[1], b0 = o0 - a0, b1 = o1 - a1;
+    const u32 la = a1 - a0, lb = b1 - b0;
+    for (u32 i = threadIdx.x; i < la; i += MG_THREADS) sm[i] = A[a0 + i];
+    for (u32 i = threadIdx.x; i < lb; i += MG_THREADS) sm[la + i] = B[b0 + i];
+    __syncthreads();
+    const Item* sa = sm;
+    const Item* sb = sm + la;
+    u32 diag = threadIdx.x * VT;
+    if (diag > la + lb) diag = la + lb;
+    u32 ai = merge_path_search<WORDS>(sa, la, sb, lb, diag, kv);
+    u32 bi = diag - ai;
+    Item r[VT];
+#pragma unroll
+    for (int i = 0; i < VT; ++i) {
+        bool take_a;
+        if (ai >= la) take_a = false;
+        else if (bi >= lb) take_a = true;
+        else take_a = !canon_less(canon_key(sb[bi], kv), canon_key(sa[ai], kv));
+        if (ai < la || bi < lb) r[i] = take_a ? sa[ai] : sb[bi];
+        if (take_a) ++ai; else ++bi;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < VT; ++i)
+        if (threadIdx.x * VT + i < la + lb) sm[threadIdx.x * VT + i] = r[i];
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < la + lb; i += MG_THREADS) out[o0 + i] = sm[i];
+}
+
+template <int WORDS>
+int merge_runs_impl(tg_ctx* ctx, const KeyView& kv, const void* d_runs, const uint64_t* run_items, uint32_t k,
+                    void* d_out, void* d_tmp) {
+    typedef typename ItemT<WORDS>::type Item;
+    constexpr int TILE = MergeCfg<WORDS>::TILE;
+    struct Run { size_t off, len; };
+    std::vector<Run> runs;
+    size_t total = 0;
+    for (uint32_t r = 0; r < k; ++r) { runs.push_back({ total, (size_t)run_items[r] }); total += run_items[r]; }
+    if (total >= (1ull << 31)) return tg_set_error(ctx, TG_ERR_TOO_LARGE, "merge: %zu items", total);
+    // drop empty runs (SortNode has none either: a File is only created for a non-empty vector, :696-704)
+    std::vector<Run> cur;
+    for (auto& r : runs) if (r.len) cur.push_back(r);
+    if (cur.empty()) return TG_OK;
+    int levels = 0;
+    for (size_t c = cur.size(); c > 1; c = (c + 1) / 2) ++levels;
+    // ping-pong so that the last level lands in d_out
+    const Item* src = (const Item*)d_runs;
+    Item* bufs[2] = { (Item*)d_out, (Item*)d_tmp };
+    int which = (levels % 2 == 0) ? 0 : 1;       // buffer written by the first level is bufs[which^...]
+    if (levels == 0) {
+        TG_CUDA(ctx, cudaMemcpyAsync(d_out, src + cur[0].off, cur[0].len * sizeof(Item), cudaMemcpyDeviceToDevice, ctx->stream));
+        return TG_OK;
+    }
+    // level l writes to bufs[(levels - 1 - l) % 2]: the last level (l = levels-1) writes bufs[0] = d_out
+    (void)which;
+    for (int l = 0; l < levels; ++l) {
+        Item* dst = bufs[(levels - 1 - l) % 2];
+        std::vector<Run> next;
+        size_t woff = 0;
+        for (size_t i = 0; i < cur.size(); i += 2) {
+            if (i + 1 < cur.size()) {
+                size_t len = cur[i].len + cur[i + 1].len;
+                u32 grid = (u32)((len + TILE - 1) / TILE);
+                TG_LAUNCH_T(ctx, TG_K_MERGE, merge2_kernel<WORDS>, grid, MG_THREADS, 0, src + cur[i].off, (u32)cur[i].len,
+                          src + cur[i + 1].off, (u32)cur[i + 1].len, dst + woff, kv);
+                next.push_back({ woff, len });
+                woff += len;
+            }
+            else {
+                TG_CUDA(ctx, cudaMemcpyAsync(dst + woff, src + cur[i].off, cur[i].len * sizeof(Item),
+                                             cudaMemcpyDeviceToDevice, ctx->stream));
+                next.push_back({ woff, cur[i].len });
+                woff += cur[i].len;
+            }
+        }
+        cur.swap(next);
+        src = dst;
+    }
+    return TG_OK;
+}
+
+void canon_splitters_from_packed(const tg_key_desc* desc, const KeyView& kv, const void* packed, uint32_t nspl,
+                                 std::vector<CanonIdx>* out) {
+    const unsigned char* p = (const unsigned char*)packed;
+    size_t s = desc->item_bytes + 8;
+    out->resize(nspl);
+    for (uint32_t j = 0; j < nspl; ++j) {
+        Canon c = canon_key_host(p + j * s, kv);
+        u64 idx;
+        memcpy(&idx, p + j * s + desc->item_bytes, 8);
+        (*out)[j] = { c.hi, c.lo, idx };
+    }
+}
+
+// splitters[i-1] = samples[(size_t)(i * double(S)/double(p))] over the (key, index)-sorted samples
+// (api/sort.hpp:357-372)
+void pick_splitters(std::vector<CanonIdx>& samples, uint32_t p, std::vector<CanonIdx>* spl) {
+    std::sort(samples.begin(), samples.end(), canonidx_less);
+    spl->clear();
+    double splitting_size = (double)samples.size() / (double)p;
+    for (uint32_t i = 1; i < p; ++i) spl->push_back(samples[(size_t)((double)i * splitting_size)]);
+}
+
+template <int WORDS>
+int sort_multi_impl(tg_ctx* ctx, const tg_key_desc* desc, const KeyView& kv, void* d_in, size_t n_local,
+                    uint64_t rng_seed, void** out_dptr, size_t* out_n) {
+    typedef typename ItemT<WORDS>::type Item;
+    const int p = ctx->nranks, me = ctx->rank;
+    const size_t s = sizeof(Item);
+    u64* h = (u64*)ctx->pinned;                      // host scratch (pinned, 1 MiB)
+    u64* d_ctl;                                      // device control-plane scratch
+    TG_TRY(tg_ws_get(ctx, WS_MISC, 1 << 16, (void**)&d_ctl));
+
+    // (1) ExPrefixSumTotal(local_items_) (api/sort.hpp:541): all-gather the shard sizes
+    h[0] = n_local;
+    TG_CUDA(ctx, cudaMemcpyAsync(d_ctl, h, 8, cudaMemcpyHostToDevice, ctx->stream));
+    TG_NCCL(ctx, ncclAllGather(d_ctl, d_ctl + 8, 1, ncclUint64, ctx->comm, ctx->stream));
+    TG_CUDA(ctx, cudaMemcpyAsync(h, d_ctl + 8, 8 * p, cudaMemcpyDeviceToHost, ctx->stream));
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<u64> n_of(p);
+    u64 total = 0, prefix = 0;
+    for (int r = 0; r < p; ++r) { n_of[r] = h[r]; if (r < me) prefix += h[r]; total += h[r]; }
+    if (total == 0) { *out_dptr = nullptr; *out_n = 0; return TG_OK; }        // :550-559
+    if (n_local >= (1u << 30)) return tg_set_error(ctx, TG_ERR_TOO_LARGE, "sort: n_local=%zu", n_local);
+
+    // (2) samples: min(n, floor(log2(n)*100)) per worker (:151-175), all-gathered instead of sent to worker 0
+    std::vector<u32> ns_of(p);
+    u32 max_s = 1;
+    for (int r = 0; r < p; ++r) {
+        u64 want = n_of[r] ? tg_sample_size(n_of[r]) : 0;
+        ns_of[r] = (u32)(want < n_of[r] ? want : n_of[r]);
+        if (ns_of[r] > max_s) max_s = ns_of[r];
+    }
+    CanonIdx* d_samp;
+    TG_TRY(tg_ws_get(ctx, WS_SAMPLES, (size_t)(p + 1) * max_s * sizeof(CanonIdx) + 4096, (void**)&d_samp));
+    CanonIdx* d_mine = d_samp + (size_t)p * max_s;
+    if (ns_of[me])
+        TG_LAUNCH(ctx, draw_samples_kernel<WORDS>, (ns_of[me] + 255) / 256, 256, 0, (const Item*)d_in, (u64)n_local, prefix,
+                  rng_seed * 0x9E3779B97F4A7C15ull + (u64)me * 0x100000000ull, ns_of[me], kv, (Item*)nullptr, d_mine);
+    TG_NCCL(ctx, ncclAllGather(d_mine, d_samp, (size_t)max_s * sizeof(CanonIdx), ncclUint8, ctx->comm, ctx->stream));
+    std::vector<CanonIdx> all((size_t)p * max_s);
+    TG_CUDA(ctx, cudaMemcpyAsync(all.data(), d_samp, all.size() * sizeof(CanonIdx), cudaMemcpyDeviceToHost, ctx->stream));
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<CanonIdx> samples, spl;
+    for (int r = 0; r < p; ++r)
+        for (u32 i = 0; i < ns_of[r]; ++i) samples.push_back(all[(size_t)r * max_s + i]);
+    pick_splitters(samples, (uint32_t)p, &spl);      // identical on every rank (same data, same order)
+    const u32 nspl = (u32)spl.size();
+
+    // (3) per-splitter tie counts on the unsorted shard, (4) local radix sort, (5) bucket boundaries
+    CanonIdx* d_spl = d_samp;       // reuse
+    u32* d_tie = (u32*)(d_ctl + 1024);
+    u64* d_bnd = d_ctl + 2048;
+    TG_CUDA(ctx, cudaMemcpyAsync(d_spl, spl.data(), nspl * sizeof(CanonIdx), cudaMemcpyHostToDevice, ctx->stream));
+    TG_CUDA(ctx, cudaMemsetAsync(d_tie, 0, 4096, ctx->stream));
+    if (n_local && nspl)
+        TG_LAUNCH(ctx, tie_count_kernel<WORDS>, ctx->sm_count * 4, 512, 0, (const Item*)d_in, (u32)n_local, prefix, kv, d_spl, nspl, d_tie);
+    void* d_tmp;
+    TG_TRY(tg_ws_get(ctx, WS_SORT_TMP, n_local * s, &d_tmp));
+    TG_TRY(tg_radix_sort_items(ctx, desc, d_in, d_tmp, n_local));
+    if (nspl) TG_LAUNCH(ctx, boundaries_kernel<WORDS>, (nspl + 63) / 64, 64, 0, (const Item*)d_in, (u32)n_local, kv, d_spl, nspl, d_tie, d_bnd);
+    TG_CUDA(ctx, cudaMemcpyAsync(h, d_bnd, 8 * nspl, cudaMemcpyDeviceToHost, ctx->stream));
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<u64> send_cnt(p), send_off(p + 1, 0);
+    {
+        u64 prev = 0;
+        for (int r = 0; r < p; ++r) {
+            u64 b = (r < p - 1) ? h[r] : n_local;
+            send_cnt[r] = b - prev;
+            prev = b;
+            send_off[r + 1] = send_off[r] + send_cnt[r];
+        }
+    }
+    // (6) count exchange: all-gather the p send counts of every rank (what the 29-byte block headers carry
+    // in the reference, data/multiplexer_header.hpp:36-72), then the Alltoallv itself
+    for (int r = 0; r < p; ++r) h[r] = send_cnt[r];
+    TG_CUDA(ctx, cudaMemcpyAsync(d_ctl, h, 8 * p, cudaMemcpyHostToDevice, ctx->stream));
+    TG_NCCL(ctx, ncclAllGather(d_ctl, d_ctl + 64, p, ncclUint64, ctx->comm, ctx->stream));
+    TG_CUDA(ctx, cudaMemcpyAsync(h, d_ctl + 64, 8 * p * p, cudaMemcpyDeviceToHost, ctx->stream));
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<u64> recv_cnt(p), recv_off(p + 1, 0);
+    for (int r = 0; r < p; ++r) { recv_cnt[r] = h[(size_t)r * p + me]; recv_off[r + 1] = recv_off[r] + recv_cnt[r]; }
+    const u64 n_recv = recv_off[p];
+    Item* d_recv;
+    TG_TRY(tg_ws_get(ctx, WS_XCHG_RECV, (n_recv + 1) * s, (void**)&d_recv));
+    TG_NCCL(ctx, ncclGroupStart());
+    for (int r = 0; r < p; ++r) {
+        if (send_cnt[r]) TG_NCCL(ctx, ncclSend((const Item*)d_in + send_off[r], send_cnt[r] * s, ncclUint8, r, ctx->comm, ctx->stream));
+        if (recv_cnt[r]) TG_NCCL(ctx, ncclRecv(d_recv + recv_off[r], recv_cnt[r] * s, ncclUint8, r, ctx->comm, ctx->stream));
+    }
+    TG_NCCL(ctx, ncclGroupEnd());
+
+    // (7) merge the p received sorted runs (source order = worker order: stable)
+    Item* d_out;
+    TG_TRY(tg_ws_get(ctx, WS_OUT, (n_recv + 1) * s, (void**)&d_out));
+    void* d_mtmp;
+    TG_TRY(tg_ws_get(ctx, WS_SORT_TMP, (n_recv + 1) * s, &d_mtmp));
+    TG_TRY(merge_runs_impl<WORDS>(ctx, kv, d_recv, (const uint64_t*)recv_cnt.data(), (uint32_t)p, d_out, d_mtmp));
+    *out_dptr = d_out;
+    *out_n = (size_t)n_recv;
+    return TG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// common/reservoir_sampling.hpp:270-275 with desired_imbalance = 0.1 (api/sort.hpp:298); note
+// 1/(0.1*0.1) == 99.99999999999999 in double, exactly as the reference computes it
+uint64_t tg_sample_size(uint64_t local_items) {
+    const double imbalance = 0.1;
+    uint64_t s = (uint64_t)(std::log2((double)local_items) * (1.0 / (imbalance * imbalance)));
+    return s > 1 ? s : 1;
+}
+
+int tg_select_splitters(const tg_key_desc* desc, void* samples, uint64_t nsamples, uint32_t p, void* out_splitters) {
+    KeyView kv;
+    if (make_key_view(desc, &kv) != TG_OK || !samples || p == 0) return TG_ERR_ARG;
+    if (nsamples == 0) return TG_OK;
+    const size_t s = desc->item_bytes + 8;
+    unsigned char* base = (unsigned char*)samples;
+    struct Ent { CanonIdx c; uint64_t src; };
+    std::vector<Ent> v(nsamples);
+    for (uint64_t i = 0; i < nsamples; ++i) {
+        Canon c = canon_key_host(base + i * s, kv);
+        u64 idx;
+        memcpy(&idx, base + i * s + desc->item_bytes, 8);
+        v[i] = { { c.hi, c.lo, idx }, i };
+    }
+    std::stable_sort(v.begin(), v.end(), [](const Ent& a, const Ent& b) { return canonidx_less(a.c, b.c); });
+    std::vector<unsigned char> sorted(nsamples * s);
+    for (uint64_t i = 0; i < nsamples; ++i) memcpy(&sorted[i * s], base + v[i].src * s, s);
+    memcpy(base, sorted.data(), sorted.size());
+    double splitting_size = (double)nsamples / (double)p;
+    for (uint32_t i = 1; i < p; ++i)
+        memcpy((unsigned char*)out_splitters + (size_t)(i - 1) * s, base + (size_t)((double)i * splitting_size) * s, s);
+    return TG_OK;
+}
+
+int tg_draw_samples(tg_ctx* ctx, const tg_key_desc* desc, const void* d_items, size_t n, uint64_t global_index_base,
+                    uint64_t rng_seed, void* out_samples_host, uint64_t* out_nsamples) {
+    KeyView kv;
+    if (!ctx || make_key_view(desc, &kv) != TG_OK || (desc->item_bytes != 8 && desc->item_bytes != 16))
+        return tg_set_error(ctx, TG_ERR_ARG, "draw_samples: unsupported descriptor");
+    uint64_t want = n ? tg_sample_size(n) : 0;
+    u32 ns = (u32)(want < n ? want : n);
+    *out_nsamples = ns;
+    if (!ns) return TG_OK;
+    unsigned char* d;
+    size_t ib = desc->item_bytes;
+    TG_TRY(tg_ws_get(ctx, WS_SAMPLES, (size_t)ns * (ib + sizeof(CanonIdx)) + 4096, (void**)&d));
+    CanonIdx* d_canon = (CanonIdx*)d;
+    unsigned char* d_items_out = d + (((size_t)ns * sizeof(CanonIdx) + 255) & ~(size_t)255);
+    if (ib == 8)
+        TG_LAUNCH(ctx, draw_samples_kernel<1>, (ns + 255) / 256, 256, 0, (const u64*)d_items, (u64)n, global_index_base, rng_seed, ns, kv, (u64*)d_items_out, d_canon);
+    else
+        TG_LAUNCH(ctx, draw_samples_kernel<2>, (ns + 255) / 256, 256, 0, (const ulonglong2*)d_items, (u64)n, global_index_base, rng_seed, ns, kv, (ulonglong2*)d_items_out, d_canon);
+    std::vector<CanonIdx> canon(ns);
+    std::vector<unsigned char> items((size_t)ns * ib);
+    TG_CUDA(ctx, cudaMemcpyAsync(canon.data(), d_canon, ns * sizeof(CanonIdx), cudaMemcpyDeviceToHost, ctx->stream));
+    TG_CUDA(ctx, cudaMemcpyAsync(items.data(), d_items_out, (size_t)ns * ib, cudaMemcpyDeviceToHost, ctx->stream));
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    unsigned char* o = (unsigned char*)out_samples_host;
+    for (u32 i = 0; i < ns; ++i) {
+        memcpy(o + (size_t)i * (ib + 8), &items[(size_t)i * ib], ib);
+        memcpy(o + (size_t)i * (ib + 8) + ib, &canon[i].idx, 8);
+    }
+    return TG_OK;
+}
+
+int tg_classify_scatter(tg_ctx* ctx, const tg_key_desc* desc, const void* d_in, size_t n, uint64_t global_index_base,
+                        const void* splitters_host, uint32_t p, void* d_out, uint64_t* out_counts) {
+    KeyView kv;
+    if (!ctx || make_key_view(desc, &kv) != TG_OK || (desc->item_bytes != 8 && desc->item_bytes != 16) || p == 0 || p > RADIX)
+        return tg_set_error(ctx, TG_ERR_ARG, "classify_scatter: unsupported descriptor or p");
+    if (n >= (1u << 30)) return tg_set_error(ctx, TG_ERR_TOO_LARGE, "classify_scatter: n=%zu", n);
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<CanonIdx> spl;
+    canon_splitters_from_packed(desc, kv, splitters_host, p - 1, &spl);
+    CanonIdx* d_spl;
+    TG_TRY(tg_ws_get(ctx, WS_SAMPLES, (size_t)p * sizeof(CanonIdx) + 256, (void**)&d_spl));
+    if (p > 1) TG_CUDA(ctx, cudaMemcpyAsync(d_spl, spl.data(), (p - 1) * sizeof(CanonIdx), cudaMemcpyHostToDevice, ctx->stream));
+    SplitterDigit fn = { d_spl, p - 1, global_index_base, kv };
+    u32* d_counts = nullptr;
+    if (desc->item_bytes == 8) TG_TRY((partition_items<1, SplitterDigit>(ctx, d_in, d_out, (u32)n, fn, &d_counts)));
+    else TG_TRY((partition_items<2, SplitterDigit>(ctx, d_in, d_out, (u32)n, fn, &d_counts)));
+    u32* hc = (u32*)ctx->pinned;
+    TG_CUDA(ctx, cudaMemcpyAsync(hc, d_counts, RADIX * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (uint32_t r = 0; r < p; ++r) out_counts[r] = hc[r];
+    return TG_OK;
+}
+
+int tg_kway_merge(tg_ctx* ctx, const tg_key_desc* desc, const void* d_runs, const uint64_t* run_items, uint32_t k,
+                  void* d_out, void* d_tmp) {
+    KeyView kv;
+    if (!ctx || make_key_view(desc, &kv) != TG_OK || (desc->item_bytes != 8 && desc->item_bytes != 16))
+        return tg_set_error(ctx, TG_ERR_ARG, "kway_merge: unsupported descriptor");
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    return desc->item_bytes == 8 ? merge_runs_impl<1>(ctx, kv, d_runs, run_items, k, d_out, d_tmp)
+                                 : merge_runs_impl<2>(ctx, kv, d_runs, run_items, k, d_out, d_tmp);
+}
+
+int tg_sort(tg_ctx* ctx, const tg_key_desc* desc, void* d_in, size_t n_local, uint64_t rng_seed, void** out_dptr, size_t* out_n) {
+    KeyView kv;
+    if (!ctx || !out_dptr || !out_n || make_key_view(desc, &kv) != TG_OK || (desc->item_bytes != 8 && desc->item_bytes != 16))
+        return tg_set_error(ctx, TG_ERR_ARG, "sort: unsupported descriptor");
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->nranks == 1) {
+        // workers_algo = 1: zero splitters, everything lands in bucket 0 (api/sort.hpp:575-579): local sort only
+        void* d_tmp;
+        TG_TRY(tg_ws_get(ctx, WS_SORT_TMP, n_local * desc->item_bytes, &d_tmp));
+        TG_TRY(tg_radix_sort_items(ctx, desc, d_in, d_tmp, n_local));
+        *out_dptr = d_in;
+        *out_n = n_local;
+        return TG_OK;
+    }
+    return desc->item_bytes == 8 ? sort_multi_impl<1>(ctx, desc, kv, d_in, n_local, rng_seed, out_dptr, out_n)
+                                 : sort_multi_impl<2>(ctx, desc, kv, d_in, n_local, rng_seed, out_dptr, out_n);
+}
+
+int tg_sort_file(tg_ctx* ctx, const tg_key_desc* desc, const tg_block* in_blocks, size_t n_in_blocks, uint64_t rng_seed,
+                 size_t* out_items) {
+    if (!ctx || !desc || !out_items) return TG_ERR_ARG;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t bytes = 0;
+    for (size_t i = 0; i < n_in_blocks; ++i) bytes += in_blocks[i].bytes;
+    if (bytes % desc->item_bytes) return tg_set_error(ctx, TG_ERR_ARG, "sort_file: %zu bytes is not a multiple of the item size", bytes);
+    void* d_in;
+    TG_TRY(tg_ws_get(ctx, WS_IN, bytes + 16, &d_in));
+    TG_TRY(tg_upload_blocks(ctx, d_in, in_blocks, n_in_blocks, nullptr));
+    void* out = nullptr;
+    size_t n_out = 0;
+    TG_TRY(tg_sort(ctx, desc, d_in, bytes / desc->item_bytes, rng_seed, &out, &n_out));
+    ctx->out_ptr = out; ctx->out_items = n_out; ctx->out_item_bytes = desc->item_bytes;
+    *out_items = n_out;
+    return TG_OK;
+}
+
+int tg_fetch_output(tg_ctx* ctx, const tg_block_mut* out_blocks, size_t n_out_blocks) {
+    if (!ctx) return TG_ERR_ARG;
+    size_t bytes = 0;
+    for (size_t i = 0; i < n_out_blocks; ++i) bytes += out_blocks[i].bytes;
+    if (bytes != ctx->out_items * ctx->out_item_bytes)
+        return tg_set_error(ctx, TG_ERR_ARG, "fetch_output: blocks hold %zu bytes, result has %zu", bytes, ctx->out_items * ctx->out_item_bytes);
+    if (bytes) TG_TRY(tg_download_blocks(ctx, ctx->out_ptr, out_blocks, n_out_blocks));
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->out_ptr = nullptr; ctx->out_items = 0;
+    return TG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,331 @@
+/*******************************************************************************
+ * thrill_b200/host/thrill_gpu_nodes.hpp — the C++ host side of the drop-in.
+ *
+ * Two DOpNode classes with exactly the StageBuilder protocol of the reference's SortNode
+ * (thrill/api/sort.hpp:64-271) and ReduceNode (thrill/api/reduce_by_key.hpp:64-211), and the front doors
+ *     thrill_gpu::Sort(dia [, std::less<T>/std::greater<T>])     <->  DIA<T>::Sort      (api/sort.hpp:800)
+ *     thrill_gpu::ReducePair(dia, std::plus<double> ...)          <->  DIA<T>::ReducePair(api/reduce_by_key.hpp:410)
+ * Everything else of the pipeline (sources, LOps, other DOps, actions, the net/data layers) is the
+ * UNMODIFIED reference library: this header only includes it.  The heavy lifting happens behind the C ABI
+ * of include/thrill_gpu.h (libthrill_gpu.so): the nodes hand the Blocks of their input data::File to
+ * tg_sort_file / tg_reduce_file and wrap the result bytes in fresh ByteBlocks of the worker's BlockPool with
+ * the geometry BlockWriter would have produced (tg_file_geometry), so children see an ordinary data::File
+ * (PushFile, thrill/api/dia_node.hpp:156-180).
+ *
+ * One Thrill worker thread = one GPU = one tg_ctx (device = Context::local_worker_id()); the NCCL id is
+ * created by worker 0 and broadcast over the reference's own control plane (ctx.net.Broadcast,
+ * net/flow_control_channel.hpp:424).  Only a closed set of (type, functor) pairs maps to a descriptor;
+ * anything else is a compile-time error (static_assert) — there is no CPU fallback inside these nodes:
+ * a user who wants the CPU path calls the stock dia.Sort() / dia.ReducePair().
+ * Requires Release builds (common::g_self_verify == false, common/config.hpp:32), which is asserted.
+ ******************************************************************************/
+#pragma once
+#ifndef THRILL_GPU_NODES_HEADER
+#define THRILL_GPU_NODES_HEADER
+
+#include <thrill/api/dia.hpp>
+#include <thrill/api/dop_node.hpp>
+#include <thrill/common/config.hpp>
+#include <thrill/data/file.hpp>
+
+#include <array>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include "../../include/thrill_gpu.h"
+
+namespace thrill_gpu {
+
+using thrill::api::Context;
+using thrill::api::DIA;
+using thrill::api::DIAMemUse;
+
+//! non-zero status of the C ABI -> die() (tlx::DieException), the reference's error path
+inline void Check(tg_ctx* c, int status, const char* what) {
+    if (status != TG_OK)
+        die("thrill_gpu: " << what << " failed: " << tg_strerror(status) << ": " << tg_last_error(c));
+}
+
+//! one tg_ctx per worker, created on first use (collective: every worker must reach its first GPU node)
+inline tg_ctx * WorkerCtx(Context& ctx) {
+    static std::mutex mutex;
+    static std::map<Context*, tg_ctx*> table;
+    {
+        std::lock_guard<std::mutex> lock(mutex);
+        auto it = table.find(&ctx);
+        if (it != table.end()) return it->second;
+    }
+    static_assert(!thrill::common::g_self_verify || true, "");
+    die_unless(!thrill::common::g_self_verify);     // Debug builds prefix every item with a typecode
+    using Id = std::array<char, 128>;
+    Id id;
+    id.fill(0);
+    if (ctx.num_workers() > 1) {
+        if (ctx.my_rank() == 0) Check(nullptr, tg_get_unique_id(id.data()), "tg_get_unique_id");
+        id = ctx.net.Broadcast(id, 0);
+    }
+    tg_ctx* c = nullptr;
+    int st = tg_init(static_cast<int>(ctx.local_worker_id()), static_cast<int>(ctx.my_rank()),
+                     static_cast<int>(ctx.num_workers()), id.data(), &c);
+    Check(c, st, "tg_init");
+    std::lock_guard<std::mutex> lock(mutex);
+    table[&ctx] = c;
+    return c;
+}
+
+/******************************************************************************/
+// descriptors of the recognised (type, functor) pairs
+
+template <typename ValueType, typename Compare, typename Enable = void>
+struct SortDesc {
+    static constexpr bool supported = false;
+};
+template <typename Compare>
+struct SortDesc<uint64_t, Compare, typename std::enable_if<
+                    std::is_same<Compare, std::less<uint64_t> >::value ||
+                    std::is_same<Compare, std::greater<uint64_t> >::value>::type>{
+    static constexpr bool supported = true;
+    static tg_key_desc make() {
+        return tg_key_desc { 8, 0, 8, TG_KEY_UINT_LE,
+                             std::is_same<Compare, std::greater<uint64_t> >::value ? 1u : 0u, 0 };
+    }
+};
+//! pair<uint64_t, 8-byte POD> ordered by .first (serialized member-wise as 16 bytes, data/serialization.hpp:67-84)
+struct LessFirst {
+    template <typename P>
+    bool operator () (const P& a, const P& b) const { return a.first < b.first; }
+};
+template <typename V>
+struct SortDesc<std::pair<uint64_t, V>, LessFirst,
+                typename std::enable_if<sizeof(V) == 8 && std::is_pod<V>::value>::type>{
+    static constexpr bool supported = true;
+    static tg_key_desc make() { return tg_key_desc { 16, 0, 8, TG_KEY_UINT_LE, 0, 1 }; }
+};
+
+template <typename Value, typename ReduceFunction>
+struct ReduceDesc {
+    static constexpr bool supported = false;
+};
+template <>
+struct ReduceDesc<double, std::plus<double> >{
+    static constexpr bool supported = true;
+    static constexpr uint32_t op = TG_OP_SUM_F64;
+};
+template <>
+struct ReduceDesc<uint64_t, std::plus<uint64_t> >{
+    static constexpr bool supported = true;
+    static constexpr uint32_t op = TG_OP_SUM_U64;
+};
+struct MinU64 { uint64_t operator () (uint64_t a, uint64_t b) const { return b < a ? b : a; } };
+struct MaxU64 { uint64_t operator () (uint64_t a, uint64_t b) const { return a < b ? b : a; } };
+template <>
+struct ReduceDesc<uint64_t, MinU64>{
+    static constexpr bool supported = true;
+    static constexpr uint32_t op = TG_OP_MIN_U64;
+};
+template <>
+struct ReduceDesc<uint64_t, MaxU64>{
+    static constexpr bool supported = true;
+    static constexpr uint32_t op = TG_OP_MAX_U64;
+};
+
+/******************************************************************************/
+// shared File <-> C ABI plumbing
+
+//! pin every Block of a File and describe it for the C ABI (replaces File::GetReader + per-item Next)
+class PinnedFileView
+{
+public:
+    PinnedFileView(const thrill::data::File& file, size_t local_worker_id) {
+        pins_.reserve(file.num_blocks());
+        blocks_.reserve(file.num_blocks());
+        for (const thrill::data::Block& b : file.blocks()) {
+            pins_.emplace_back(b.PinWait(local_worker_id));
+            const thrill::data::PinnedBlock& pb = pins_.back();
+            blocks_.push_back(tg_block { pb.data_begin(), pb.size() });
+        }
+    }
+    const tg_block * data() const { return blocks_.data(); }
+    size_t size() const { return blocks_.size(); }
+
+private:
+    std::vector<thrill::data::PinnedBlock> pins_;
+    std::vector<tg_block> blocks_;
+};
+
+//! allocate ByteBlocks with BlockWriter's geometry, let the GPU result land in them, append them to `out`
+inline void FetchIntoFile(tg_ctx* c, Context& ctx, size_t num_items, uint32_t item_bytes,
+                          thrill::data::File& out) {
+    size_t nblocks = tg_file_geometry(num_items, item_bytes, thrill::data::start_block_size,
+                                      thrill::data::default_block_size, nullptr, 0);
+    std::vector<tg_block_geom> geom(nblocks);
+    tg_file_geometry(num_items, item_bytes, thrill::data::start_block_size,
+                     thrill::data::default_block_size, geom.data(), geom.size());
+    std::vector<thrill::data::PinnedByteBlockPtr> bytes;
+    std::vector<tg_block_mut> targets;
+    bytes.reserve(nblocks);
+    for (const tg_block_geom& g : geom) {
+        // power-of-two ByteBlock of at least g.bytes, as BlockWriter::AllocateBlock requests them
+        size_t cap = thrill::data::start_block_size;
+        while (cap < g.bytes) cap *= 2;
+        bytes.emplace_back(ctx.block_pool().AllocateByteBlock(cap, ctx.local_worker_id()));
+        targets.push_back(tg_block_mut { bytes.back()->data(), static_cast<size_t>(g.bytes) });
+    }
+    Check(c, tg_fetch_output(c, targets.data(), targets.size()), "tg_fetch_output");
+    for (size_t i = 0; i < nblocks; ++i) {
+        thrill::data::PinnedBlock pb(std::move(bytes[i]), 0, geom[i].bytes, geom[i].first_item,
+                                     geom[i].num_items, /* typecode_verify */ false);
+        out.AppendBlock(std::move(pb).MoveToBlock());
+    }
+}
+
+/******************************************************************************/
+
+template <typename ValueType>
+class GpuSortNode final : public thrill::api::DOpNode<ValueType>
+{
+    using Super = thrill::api::DOpNode<ValueType>;
+    using Super::context_;
+
+public:
+    template <typename ParentDIA>
+    GpuSortNode(const ParentDIA& parent, const tg_key_desc& desc)
+        : Super(parent.ctx(), "GpuSort", { parent.id() }, { parent.node() }),
+          desc_(desc), parent_stack_empty_(ParentDIA::stack_empty) {
+        // hook the per-item PreOp exactly as SortNode does (api/sort.hpp:131-136)
+        auto pre_op_fn = [this](const ValueType& input) { unsorted_writer_.Put(input); };
+        auto lop_chain = parent.stack().push(pre_op_fn).fold();
+        parent.node()->AddChild(this, lop_chain);
+    }
+
+    void StartPreOp(size_t /* parent_index */) final { unsorted_writer_ = unsorted_file_.GetWriter(); }
+
+    //! whole-File hand-off: the bulk path (api/sort.hpp:151-175)
+    bool OnPreOpFile(const thrill::data::File& file, size_t /* parent_index */) final {
+        if (!parent_stack_empty_) return false;
+        unsorted_file_ = file.Copy();
+        return true;
+    }
+
+    void StopPreOp(size_t /* parent_index */) final { unsorted_writer_.Close(); }
+
+    DIAMemUse ExecuteMemUse() final { return DIAMemUse::Max(); }
+
+    //! MainOp (api/sort.hpp:537-663) + the local sort / merge, all behind tg_sort_file.  Collective.
+    void Execute() final {
+        tg_ctx* c = WorkerCtx(context_);
+        size_t out_items = 0;
+        {
+            PinnedFileView view(unsorted_file_, context_.local_worker_id());
+            Check(c, tg_sort_file(c, &desc_, view.data(), view.size(), context_.rng_(), &out_items), "tg_sort_file");
+        }
+        unsorted_file_.Clear();
+        FetchIntoFile(c, context_, out_items, sizeof(ValueType), sorted_file_);
+    }
+
+    DIAMemUse PushDataMemUse() final { return 0; }
+
+    //! one sorted run per worker: always the files_.size() == 1 branch of SortNode::PushData (:224-227)
+    void PushData(bool consume) final { this->PushFile(sorted_file_, consume); }
+
+    void Dispose() final { sorted_file_.Clear(); }
+
+private:
+    tg_key_desc desc_;
+    const bool parent_stack_empty_;
+    thrill::data::File unsorted_file_ { context_.GetFile(this) };
+    thrill::data::File::Writer unsorted_writer_;
+    thrill::data::File sorted_file_ { context_.GetFile(this) };
+};
+
+template <typename ValueType>
+class GpuReduceNode final : public thrill::api::DOpNode<ValueType>
+{
+    using Super = thrill::api::DOpNode<ValueType>;
+    using Super::context_;
+
+public:
+    template <typename ParentDIA>
+    GpuReduceNode(const ParentDIA& parent, const tg_kv_desc& desc)
+        : Super(parent.ctx(), "GpuReducePair", { parent.id() }, { parent.node() }),
+          desc_(desc), parent_stack_empty_(ParentDIA::stack_empty) {
+        // ReduceNode inserts each item into the pre-phase table (api/reduce_by_key.hpp:126-133); the GPU pre
+        // phase wants the whole shard, so items are collected in a File first
+        auto pre_op_fn = [this](const ValueType& input) { input_writer_.Put(input); };
+        auto lop_chain = parent.stack().push(pre_op_fn).fold();
+        parent.node()->AddChild(this, lop_chain);
+    }
+
+    DIAMemUse PreOpMemUse() final { return DIAMemUse::Max(); }
+
+    void StartPreOp(size_t /* parent_index */) final { input_writer_ = input_file_.GetWriter(); }
+
+    bool OnPreOpFile(const thrill::data::File& file, size_t /* parent_index */) final {
+        if (!parent_stack_empty_) return false;
+        input_file_ = file.Copy();
+        return true;
+    }
+
+    //! pre phase flush + exchange + post phase (api/reduce_by_key.hpp:157-211) behind tg_reduce_file.  Collective.
+    void StopPreOp(size_t /* parent_index */) final {
+        input_writer_.Close();
+        tg_ctx* c = WorkerCtx(context_);
+        size_t out_items = 0;
+        {
+            PinnedFileView view(input_file_, context_.local_worker_id());
+            Check(c, tg_reduce_file(c, &desc_, view.data(), view.size(), &out_items), "tg_reduce_file");
+        }
+        input_file_.Clear();
+        FetchIntoFile(c, context_, out_items, sizeof(ValueType), reduced_file_);
+    }
+
+    void Execute() final { }
+
+    DIAMemUse PushDataMemUse() final { return 0; }
+
+    void PushData(bool consume) final { this->PushFile(reduced_file_, consume); }
+
+    void Dispose() final { reduced_file_.Clear(); }
+
+private:
+    tg_kv_desc desc_;
+    const bool parent_stack_empty_;
+    thrill::data::File input_file_ { context_.GetFile(this) };
+    thrill::data::File::Writer input_writer_;
+    thrill::data::File reduced_file_ { context_.GetFile(this) };
+};
+
+/******************************************************************************/
+// front doors (same argument meaning as DIA<T>::Sort / DIA<T>::ReducePair)
+
+template <typename ValueType, typename Stack, typename CompareFunction = std::less<ValueType> >
+auto Sort(const DIA<ValueType, Stack>& dia, const CompareFunction& /* compare_function */ = CompareFunction()) {
+    static_assert(SortDesc<ValueType, CompareFunction>::supported,
+                  "thrill_gpu::Sort: this (ValueType, CompareFunction) pair has no GPU descriptor; "
+                  "use the stock dia.Sort(cmp)");
+    assert(dia.IsValid());
+    auto node = tlx::make_counting<GpuSortNode<ValueType> >(
+        dia, SortDesc<ValueType, CompareFunction>::make());
+    return DIA<ValueType>(node);
+}
+
+template <typename Key, typename Value, typename Stack, typename ReduceFunction>
+auto ReducePair(const DIA<std::pair<Key, Value>, Stack>& dia, const ReduceFunction& /* reduce_function */) {
+    static_assert(std::is_same<Key, uint64_t>::value && sizeof(Value) == 8 &&
+                  ReduceDesc<Value, ReduceFunction>::supported,
+                  "thrill_gpu::ReducePair: this (Key, Value, ReduceFunction) has no GPU descriptor; "
+                  "use the stock dia.ReducePair(fn)");
+    assert(dia.IsValid());
+    using ValueType = std::pair<Key, Value>;
+    auto node = tlx::make_counting<GpuReduceNode<ValueType> >(
+        dia, tg_kv_desc { 16, ReduceDesc<Value, ReduceFunction>::op });
+    return DIA<ValueType>(node);
+}
+
+} // namespace thrill_gpu
+
+#endif // !THRILL_GPU_NODES_HEADER
