@@ -1,0 +1,21 @@
+"""N>1 on real GPUs: launches tests/multi_gpu_worker.py with one process per GPU (torch.distributed.run) and
+requires bit-exact parity with the reference outputs.  Needs >= 2 GPUs (gpurun --gpus 2); skipped otherwise."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_collective_operators_on_n_gpus(world):
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(29600 + world), os.path.join(HERE, "multi_gpu_worker.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=1500)
+    assert res.returncode == 0 and "MULTI_GPU_PARITY_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-5000:]
