@@ -72,6 +72,14 @@ def main():
         same = cat["key"][1:] == cat["key"][:-1]
         assert np.all(cat["val"][1:][same] > cat["val"][:-1][same]), "SortStable order violated"
 
+    # ---- TeraSort records (100 B, 10-byte key) vs the reference ----
+    dia = api.Generate(ctx, 20000, lambda idx: O.gen_records(int(idx[0]) if len(idx) else 0, len(idx)), dtype=None)
+    parts = gather(dia.Sort().items, world)
+    if rank == 0:
+        cat = np.concatenate(parts)
+        assert np.array_equal(cat[:8], g["terasort_20000_w3_head"])
+        assert sha(cat) == str(g["terasort_20000_w3_sha256"]), "terasort: differs from the reference"
+
     # ---- ReducePair: Zipf f64 sums vs the reference (tolerance) and exact mode (bit-exact), ownership ----
     cdf = O.zipf_cdf(4096)
     for exact, key, tol in ((0, "reduce_f64_zipf_u4096_200000_w3", 1e-9), (1, "reduce_f64_exact_zipf_u4096_200000_w4", 0.0)):

@@ -166,3 +166,23 @@ def test_sort_operator_single_gpu_golden_and_file_codec(ctx):
     ctx.ck(ctx.L.tg_fetch_output(ctx.h, ob, ng))
     assert sha(out) == str(g["sort_uniform_1000000_w4_sha256"])
     assert np.array_equal(out, O.sort_items(keys).view(np.uint64))
+
+
+def test_terasort_records_single_gpu_golden(ctx):
+    """cfg4 shape (reduced): 100-byte records, 10-byte big-endian key, vs the unmodified reference's output"""
+    from thrill_b200 import api
+    g = golden()
+    rec = O.gen_records(0, 20000)
+    actx = api.Context.__new__(api.Context)
+    actx._rank, actx._n, actx.tg, actx.rng_seed, actx._op_counter = 0, 1, ctx, 1, 0
+    out = api.DIA(actx, rec).Sort().items
+    assert out.shape == (20000, 100)
+    assert np.array_equal(out[:8], g["terasort_20000_w3_head"])
+    assert sha(out) == str(g["terasort_20000_w3_sha256"])
+    # duplicates-heavy keys: stable order == the oracle's stable sort
+    rec2 = O.gen_records(0, 50000)
+    rec2[:, :9] = 0
+    rec2[:, 9] = np.random.RandomState(3).randint(0, 4, size=50000)
+    out2 = api.DIA(actx, rec2).Sort().items
+    ref2 = O.sort_items(rec2, O.RECORD_DESC).reshape(-1, 100)
+    assert np.array_equal(out2, ref2)

@@ -151,6 +151,10 @@ class DIA(object):
             return capi.KeyDesc(8, 0, 8, capi.KEY_UINT_LE, desc, 0), np.uint64
         if it.ndim == 1 and it.dtype == KV:
             return capi.KeyDesc(16, 0, 8, capi.KEY_UINT_LE, desc, 0), KV
+        if it.ndim == 2 and it.dtype == np.uint8 and it.shape[1] == 100 and not desc:
+            # TeraSort Record{uint8 key[10]; uint8 value[90]}, operator< = lexicographic on the key
+            # (examples/terasort/terasort.cpp:31-42)
+            return capi.KeyDesc(100, 0, 10, capi.KEY_BYTES_BE, 0, 0), None
         raise capi.ThrillGpuError("Sort: item type %r/%r is not supported by the GPU path" % (it.dtype, it.shape))
 
     def Sort(self, compare_function=None, _pinned_out=None):

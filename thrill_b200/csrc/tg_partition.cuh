@@ -10,6 +10,8 @@
 // (re-used) landing buffer and written out so that consecutive threads write consecutive addresses.
 // HBM traffic: read n*s + write n*s + ~3 % look-back state.
 #pragma once
+#include <stdlib.h>
+
 #include "tg_common.cuh"
 
 namespace tgp {
@@ -65,7 +67,7 @@ struct SweepCfg {
     static constexpr int TILE = THREADS * ITEMS;             // items per tile
     static constexpr int TILE_BYTES = TILE * ITEM_BYTES;     // 64 KB at 512 threads
     static constexpr int NWARPS = THREADS / 32;
-    static constexpr int SMEM = 2 * TILE_BYTES + NWARPS * RADIX * 4 + 2 * RADIX * 4 + 64 + 16 + TILE + 256;
+    static constexpr int SMEM = 2 * TILE_BYTES + 2 * NWARPS * RADIX * 4 + 2 * RADIX * 4 + 64 + 16 + TILE + 256;
 };
 
 // per-bucket counts of one digit function (the pre-pass of a stand-alone partition)
@@ -117,29 +119,37 @@ static __global__ void scan_hist_kernel(const u32* __restrict__ ghist, u32* __re
     }
 }
 
-template <int WORDS, int THREADS, class DigitFn>
-__global__ void __launch_bounds__(THREADS, 1)
+template <int WORDS, int THREADS, int MINB, int RANK, class DigitFn>
+__global__ void __launch_bounds__(THREADS, MINB)
 partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename ItemT<WORDS>::type* __restrict__ out,
-                 u32 n, DigitFn fn, const u32* __restrict__ gbase, u32* __restrict__ status) {
+                 u32 n, const DigitFn fn_param, const u32* __restrict__ gbase, u32* __restrict__ status) {
     typedef typename ItemT<WORDS>::type Item;
     typedef SweepCfg<WORDS, THREADS> C;
     constexpr int ITEMS = C::ITEMS, TILE = C::TILE, NWARPS = C::NWARPS;
     constexpr int LB = 8;       // look-back batch: predecessors fetched concurrently
 
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char* sp = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
-    Item* buf0 = (Item*)sp;
-    Item* buf1 = (Item*)(sp + C::TILE_BYTES);
-    u32* whist = (u32*)(sp + 2 * C::TILE_BYTES);              // [NWARPS][RADIX]
-    u32* bin_start = whist + NWARPS * RADIX;                  // [RADIX]
-    u32* goff = bin_start + RADIX;                            // [RADIX]
-    u32* warp_tot = goff + RADIX;                             // [16]
-    u64* mbar = (u64*)(warp_tot + 16);                        // [2]
-    unsigned char* dig = (unsigned char*)(mbar + 2);          // [TILE], only if DigitFn::kStoreDigit
+    // plain pointer arithmetic on the shared array keeps the shared address space (LDS/STS, 32-bit addresses)
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    Item* const buf0 = reinterpret_cast<Item*>(smem_raw);
+    Item* const buf1 = reinterpret_cast<Item*>(smem_raw + C::TILE_BYTES);
+    u32* const whist = reinterpret_cast<u32*>(smem_raw + 2 * C::TILE_BYTES);     // [NWARPS][RADIX]
+    u32* const goff = whist + NWARPS * RADIX;                                    // [RADIX]
+    u32* const warp_tot = goff + RADIX;                                          // [16]
+    u64* const mbar = reinterpret_cast<u64*>(warp_tot + 16);                     // [2]
+    u32* const wmask = reinterpret_cast<u32*>(mbar + 2);                         // [NWARPS][RADIX] (RANK != 0)
+    unsigned char* const dig = reinterpret_cast<unsigned char*>(wmask + NWARPS * RADIX);   // [TILE], only if kStoreDigit
 
+    const DigitFn fn = fn_param;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 num_tiles = (n + TILE - 1) / TILE;
     const u32 lt = lanemask_lt();
+    u32* const whist_w = whist + warp * RADIX;
+    u32* const wmask_w = wmask + warp * RADIX;
+    const u32 wbase = warp * 32 * ITEMS;
+    if (RANK != 0) {
+#pragma unroll
+        for (int i = 0; i < RADIX / 32; ++i) wmask_w[i * 32 + lane] = 0;
+    }
 
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
@@ -156,8 +166,8 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
 
     for (u32 it = 0; t < num_tiles; t += gridDim.x, ++it) {
         const int cur = it & 1;
-        Item* buf = cur ? buf1 : buf0;
-        Item* nbuf = cur ? buf0 : buf1;
+        Item* const buf = cur ? buf1 : buf0;
+        Item* const nbuf = cur ? buf0 : buf1;
         const u32 tile_base = t * TILE;
         const bool full_tile = (size_t)tile_base + TILE <= n;
         const u32 tile_valid = full_tile ? (u32)TILE : n - tile_base;
@@ -173,15 +183,15 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
         }
         // zero this warp's private digit counters
 #pragma unroll
-        for (int i = lane; i < RADIX; i += 32) whist[warp * RADIX + i] = 0;
+        for (int i = 0; i < RADIX / 32; ++i) whist_w[i * 32 + lane] = 0;
 
         // ---- items to registers: warp w owns tile positions [w*32*ITEMS, (w+1)*32*ITEMS), round-striped
         Item key[ITEMS];
-        const u32 wbase = warp * 32 * ITEMS;
         if (full_tile) {
             mbar_wait(&mbar[cur], (it >> 1) & 1);
+            const Item* src = buf + wbase + lane;
 #pragma unroll
-            for (int i = 0; i < ITEMS; ++i) key[i] = buf[wbase + i * 32 + lane];
+            for (int i = 0; i < ITEMS; ++i) key[i] = src[i * 32];
         }
         else {
 #pragma unroll
@@ -199,16 +209,25 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) {
                 u32 d = fn(key[i], tile_base + wbase + i * 32 + lane);
-                mydig[i] = (unsigned char)d;
-                u32 peers = match_digit<false>(d, true);
-                int leader = __ffs(peers) - 1;
-                u32 old = 0;
-                if (lane == leader) {
-                    old = whist[warp * RADIX + d];
-                    whist[warp * RADIX + d] = old + __popc(peers);
+                if (DigitFn::kStoreDigit) mydig[i] = (unsigned char)d;
+                u32 peers;
+                if (RANK == 0 || (RANK == 2 && (i & 1))) peers = match_digit<false>(d, true);
+                else {
+                    // warp-private mask table: one native 32-bit shared-memory atomic per key instead of 8 ballots
+                    atomicOr(&wmask_w[d], 1u << lane);
+                    __syncwarp();
+                    peers = wmask_w[d];
+                    __syncwarp();
                 }
-                old = __shfl_sync(0xffffffffu, old, leader);
-                rank[i] = (unsigned short)(old + __popc(peers & lt));
+                u32 below = peers & lt;
+                u32 old = 0;
+                if (below == 0) {                       // lowest lane of its group
+                    if (!(RANK == 0 || (RANK == 2 && (i & 1)))) wmask_w[d] = 0;
+                    old = whist_w[d];
+                    whist_w[d] = old + __popc(peers);
+                }
+                old = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1);
+                rank[i] = (unsigned short)(old + __popc(below));
                 __syncwarp();
             }
         }
@@ -218,32 +237,26 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
                 u32 p = wbase + i * 32 + lane;
                 bool valid = p < tile_valid;
                 u32 d = valid ? fn(key[i], tile_base + p) : 0u;
-                mydig[i] = (unsigned char)d;
+                if (DigitFn::kStoreDigit) mydig[i] = (unsigned char)d;
                 u32 peers = match_digit<true>(d, valid);
-                int leader = __ffs(peers) - 1;
+                u32 below = peers & lt;
                 u32 old = 0;
-                if (lane == leader && valid) {
-                    old = whist[warp * RADIX + d];
-                    whist[warp * RADIX + d] = old + __popc(peers);
+                if (below == 0 && valid) {
+                    old = whist_w[d];
+                    whist_w[d] = old + __popc(peers);
                 }
-                old = __shfl_sync(0xffffffffu, old, leader);
-                rank[i] = (unsigned short)(old + __popc(peers & lt));
+                old = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1);
+                rank[i] = (unsigned short)(old + __popc(below));
                 __syncwarp();
             }
         }
         __syncthreads();      // all items are in registers (buf is free), all warp counters final
 
-        // ---- per-digit tile count, warp offsets, tile-local digit starts, publish PARTIAL
-        u32 count = 0;
+        // ---- per-digit tile count; publish PARTIAL as early as possible; tile-local digit starts
+        u32 count = 0, my_start = 0;
         if (tid < RADIX) {
-            u32 sum = 0;
 #pragma unroll
-            for (int w = 0; w < NWARPS; ++w) {
-                u32 c = whist[w * RADIX + tid];
-                whist[w * RADIX + tid] = sum;
-                sum += c;
-            }
-            count = sum;
+            for (int w = 0; w < NWARPS; ++w) count += whist[w * RADIX + tid];
             st_relaxed_u32(&status[(size_t)t * RADIX + tid], count | (t == 0 ? FLAG_INCL : FLAG_PARTIAL));
             u32 incl = count;
 #pragma unroll
@@ -252,13 +265,19 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
                 if (lane >= o) incl += v;
             }
             if (lane == 31) warp_tot[warp] = incl;
-            bin_start[tid] = incl - count;       // completed below with the preceding warps' totals
+            my_start = incl - count;             // completed below with the preceding warps' totals
         }
         __syncthreads();
         if (tid < RADIX) {
-            u32 add = 0;
-            for (int w = 0; w < warp; ++w) add += warp_tot[w];
-            bin_start[tid] += add;
+            for (int w = 0; w < warp; ++w) my_start += warp_tot[w];
+            // warp counters -> tile-local write positions of each (warp, digit) group
+            u32 off = my_start;
+#pragma unroll
+            for (int w = 0; w < NWARPS; ++w) {
+                u32 c = whist[w * RADIX + tid];
+                whist[w * RADIX + tid] = off;
+                off += c;
+            }
         }
         __syncthreads();
 
@@ -285,16 +304,16 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
                 }
                 st_relaxed_u32(&status[(size_t)t * RADIX + tid], (excl + count) | FLAG_INCL);
             }
-            goff[tid] = gbase[tid] + excl - bin_start[tid];
+            goff[tid] = gbase[tid] + excl - my_start;
         }
 
         // ---- scatter registers -> digit-ordered exchange buffer (reuses the landing buffer)
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
             u32 p = wbase + i * 32 + lane;
-            if (p < tile_valid) {
+            if (full_tile || p < tile_valid) {
                 u32 d = DigitFn::kStoreDigit ? (u32)mydig[i] : fn(key[i], tile_base + p);
-                u32 q = bin_start[d] + whist[warp * RADIX + d] + rank[i];
+                u32 q = whist_w[d] + rank[i];
                 buf[q] = key[i];
                 if (DigitFn::kStoreDigit) dig[q] = (unsigned char)d;
             }
@@ -302,13 +321,16 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
         __syncthreads();
 
         // ---- coalesced write-out: consecutive threads write consecutive addresses inside a digit run
+        {
+            Item* const outp = out + tid;
+            const Item* const bufp = buf + tid;
 #pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-            u32 p = i * THREADS + tid;
-            if (p < tile_valid) {
-                Item v = buf[p];
-                u32 d = DigitFn::kStoreDigit ? (u32)dig[p] : fn(v, 0);
-                out[goff[d] + p] = v;
+            for (int i = 0; i < ITEMS; ++i) {
+                if (full_tile || (u32)(i * THREADS + tid) < tile_valid) {
+                    Item v = bufp[i * THREADS];
+                    u32 d = DigitFn::kStoreDigit ? (u32)dig[i * THREADS + tid] : fn(v, 0);
+                    outp[goff[d] + i * THREADS] = v;
+                }
             }
         }
         __syncthreads();      // exchange buffer is re-armed as the TMA landing buffer two iterations later
@@ -322,28 +344,67 @@ __global__ void copy_items_kernel(const typename ItemT<WORDS>::type* __restrict_
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = in[i];
 }
 
-constexpr int SWEEP_THREADS = 512;
+// launch configurations (threads per CTA, CTAs per SM); selected once per process, TG_SWEEP_CFG overrides
+struct SweepVariant { int threads, minb; };
+constexpr SweepVariant kSweepVariants[] = { { 512, 1 }, { 256, 2 }, { 256, 3 }, { 384, 2 } };
+inline int sweep_cfg() {
+    static int cfg = -1;
+    if (cfg < 0) {
+        const char* e = getenv("TG_SWEEP_CFG");
+        cfg = e ? atoi(e) : 0;
+        if (cfg < 0 || cfg > 3) cfg = 0;
+    }
+    return cfg;
+}
+template <int WORDS>
+inline u32 num_tiles_for(size_t n) {
+    u32 tile = (u32)kSweepVariants[sweep_cfg()].threads * (16 / WORDS);
+    return (u32)((n + tile - 1) / tile);
+}
+
+inline int rank_mode() {
+    static int m = -1;
+    if (m < 0) {
+        const char* e = getenv("TG_RANK_MODE");
+        m = e ? atoi(e) : 0;
+        if (m < 0 || m > 2) m = 0;
+    }
+    return m;
+}
+
+template <int WORDS, int THREADS, int MINB, int RANK, class DigitFn>
+int launch_partition_v(tg_ctx* ctx, const void* in, void* out, u32 n, const DigitFn& fn, const u32* gbase, u32* status) {
+    typedef typename ItemT<WORDS>::type Item;
+    typedef SweepCfg<WORDS, THREADS> C;
+    auto kern = partition_kernel<WORDS, THREADS, MINB, RANK, DigitFn>;
+    static int ctas_per_sm = 0;          // one per template instantiation
+    if (!ctas_per_sm) {
+        TG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        // the look-back needs every CTA of the grid resident: size the grid from the real occupancy
+        TG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, THREADS, C::SMEM));
+        if (ctas_per_sm < 1) return tg_set_error(ctx, TG_ERR_CUDA, "partition kernel does not fit on an SM");
+        if (ctas_per_sm > MINB) ctas_per_sm = MINB;
+    }
+    u32 num_tiles = (n + C::TILE - 1) / C::TILE;
+    int grid = ctx->sm_count * ctas_per_sm;
+    if (grid > (int)num_tiles) grid = (int)num_tiles;
+    TG_LAUNCH_T(ctx, TG_K_PARTITION, kern, grid, THREADS, C::SMEM, (const Item*)in, (Item*)out, n, fn, gbase, status);
+    return TG_OK;
+}
 
 // launch one partition pass with precomputed global bases (status must be zeroed, num_tiles*RADIX words)
 template <int WORDS, class DigitFn>
 int launch_partition(tg_ctx* ctx, const void* in, void* out, u32 n, const DigitFn& fn, const u32* gbase, u32* status) {
-    typedef typename ItemT<WORDS>::type Item;
-    typedef SweepCfg<WORDS, SWEEP_THREADS> C;
-    auto kern = partition_kernel<WORDS, SWEEP_THREADS, DigitFn>;
-    static bool attr_set = false;          // one per template instantiation
-    if (!attr_set) {
-        TG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        attr_set = true;
+    const int rm = rank_mode();
+    switch (sweep_cfg()) {
+    case 1: return launch_partition_v<WORDS, 256, 2, 0, DigitFn>(ctx, in, out, n, fn, gbase, status);
+    case 2: return launch_partition_v<WORDS, 256, 3, 0, DigitFn>(ctx, in, out, n, fn, gbase, status);
+    case 3: return launch_partition_v<WORDS, 384, 2, 0, DigitFn>(ctx, in, out, n, fn, gbase, status);
+    default:
+        if (rm == 1) return launch_partition_v<WORDS, 512, 1, 1, DigitFn>(ctx, in, out, n, fn, gbase, status);
+        if (rm == 2) return launch_partition_v<WORDS, 512, 1, 2, DigitFn>(ctx, in, out, n, fn, gbase, status);
+        return launch_partition_v<WORDS, 512, 1, 0, DigitFn>(ctx, in, out, n, fn, gbase, status);
     }
-    u32 num_tiles = (n + C::TILE - 1) / C::TILE;
-    int grid = ctx->sm_count < (int)num_tiles ? ctx->sm_count : (int)num_tiles;
-    TG_LAUNCH_T(ctx, TG_K_PARTITION, kern, grid, SWEEP_THREADS, C::SMEM, (const Item*)in, (Item*)out, n, fn, gbase, status);
-    return TG_OK;
-}
-
-template <int WORDS>
-inline u32 num_tiles_for(size_t n) {
-    return (u32)((n + SweepCfg<WORDS, SWEEP_THREADS>::TILE - 1) / SweepCfg<WORDS, SWEEP_THREADS>::TILE);
 }
 
 // stand-alone stable partition of n items into <= RADIX buckets: count pre-pass, scan, partition.

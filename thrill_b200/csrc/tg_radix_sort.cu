@@ -22,34 +22,103 @@ struct PassList {
     u32 flip;                           // RADIX-1 for descending order
 };
 
-// histogram of every digit position from one read of the input
+// histogram of every digit position from one read of the input.  Four items per thread in flight; digit
+// positions on which the whole warp agrees (constant high bytes, Zipf keys) are detected with two REDUX.OR per
+// item word and cost one shared-memory atomic per warp instead of 32 conflicting ones.
 template <int WORDS>
 __global__ void __launch_bounds__(512) radix_hist_kernel(const typename ItemT<WORDS>::type* __restrict__ in, size_t n,
                                                          PassList pl, u32* __restrict__ ghist) {
+    typedef typename ItemT<WORDS>::type Item;
+    constexpr int U = 4;
     extern __shared__ u32 sh[];      // [npass][RADIX]
     for (int i = threadIdx.x; i < pl.npass * RADIX; i += blockDim.x) sh[i] = 0;
     __syncthreads();
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t base = (size_t)blockIdx.x * blockDim.x; base < n; base += stride) {
-        size_t i = base + threadIdx.x;
-        bool valid = i < n;
-        typename ItemT<WORDS>::type v;
-        if (valid) v = in[i];
-        u32 act = __ballot_sync(0xffffffffu, valid);
-        if (!valid) continue;
+    const size_t stride = (size_t)gridDim.x * blockDim.x * U;
+    const u32 lane = lane_id();
+    for (size_t base = (size_t)blockIdx.x * blockDim.x * U; base < n; base += stride) {
+        Item v[U];
+        bool valid[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            size_t i = base + (size_t)u * blockDim.x + threadIdx.x;
+            valid[u] = i < n;
+            if (valid[u]) v[u] = in[i];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (__all_sync(0xffffffffu, valid[u])) {
+                u64 diff[WORDS];
+#pragma unroll
+                for (int w = 0; w < WORDS; ++w) {
+                    u64 x = item_word(v[u], w);
+                    u64 x0 = __shfl_sync(0xffffffffu, x, 0);
+                    u64 d = x ^ x0;
+                    u32 lo = __reduce_or_sync(0xffffffffu, (u32)d), hi = __reduce_or_sync(0xffffffffu, (u32)(d >> 32));
+                    diff[w] = ((u64)hi << 32) | lo;
+                }
 #pragma unroll 1
-        for (int p = 0; p < pl.npass; ++p) {
-            u32 d = ((u32)(item_word(v, pl.word[p]) >> pl.shift[p]) & (RADIX - 1)) ^ pl.flip;
-            // heavily duplicated digit positions (constant high bytes, Zipf keys): one atomic per warp
-            u32 d0 = __shfl_sync(act, d, __ffs(act) - 1);
-            if (__all_sync(act, d == d0)) {
-                if (lane_id() == (u32)(__ffs(act) - 1)) atomicAdd(&sh[p * RADIX + d], __popc(act));
+                for (int p = 0; p < pl.npass; ++p) {
+                    int w = pl.word[p], shf = pl.shift[p];
+                    u32 d = ((u32)(item_word(v[u], w) >> shf) & (RADIX - 1)) ^ pl.flip;
+                    bool uniform = (((WORDS == 2 && w) ? diff[WORDS - 1] : diff[0]) >> shf & 0xffull) == 0;
+                    if (uniform) { if (lane == 0) atomicAdd(&sh[p * RADIX + d], 32u); }
+                    else atomicAdd(&sh[p * RADIX + d], 1u);
+                }
             }
-            else atomicAdd(&sh[p * RADIX + d], 1u);
+            else if (valid[u]) {
+#pragma unroll 1
+                for (int p = 0; p < pl.npass; ++p) {
+                    u32 d = ((u32)(item_word(v[u], pl.word[p]) >> pl.shift[p]) & (RADIX - 1)) ^ pl.flip;
+                    atomicAdd(&sh[p * RADIX + d], 1u);
+                }
+            }
         }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < pl.npass * RADIX; i += blockDim.x)
+        if (sh[i]) atomicAdd(&ghist[i], sh[i]);
+}
+
+// fast path of the histogram for plain u64 keys (8 digits = the 8 bytes of the key): constant shifts, fully unrolled
+__global__ void __launch_bounds__(512) radix_hist_u64_kernel(const u64* __restrict__ in, size_t n, u32 flip, u32* __restrict__ ghist) {
+    constexpr int U = 4;
+    __shared__ u32 sh[8 * RADIX];
+    for (int i = threadIdx.x; i < 8 * RADIX; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const size_t stride = (size_t)gridDim.x * blockDim.x * U;
+    const u32 lane = lane_id();
+    for (size_t base = (size_t)blockIdx.x * blockDim.x * U; base < n; base += stride) {
+        u64 v[U];
+        bool valid[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            size_t i = base + (size_t)u * blockDim.x + threadIdx.x;
+            valid[u] = i < n;
+            v[u] = valid[u] ? in[i] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (__all_sync(0xffffffffu, valid[u])) {
+                u64 x0 = __shfl_sync(0xffffffffu, v[u], 0);
+                u64 df = v[u] ^ x0;
+                u32 dlo = __reduce_or_sync(0xffffffffu, (u32)df), dhi = __reduce_or_sync(0xffffffffu, (u32)(df >> 32));
+                u32 klo = (u32)v[u], khi = (u32)(v[u] >> 32);
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    u32 w = p < 4 ? klo : khi, dw = p < 4 ? dlo : dhi;
+                    u32 d = ((w >> (8 * (p & 3))) & 0xffu) ^ flip;
+                    if (((dw >> (8 * (p & 3))) & 0xffu) == 0) { if (lane == 0) atomicAdd(&sh[p * RADIX + d], 32u); }
+                    else atomicAdd(&sh[p * RADIX + d], 1u);
+                }
+            }
+            else if (valid[u]) {
+#pragma unroll
+                for (int p = 0; p < 8; ++p) atomicAdd(&sh[p * RADIX + (((u32)(v[u] >> (8 * p)) & 0xffu) ^ flip)], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 8 * RADIX; i += blockDim.x)
         if (sh[i]) atomicAdd(&ghist[i], sh[i]);
 }
 
@@ -83,7 +152,12 @@ int radix_sort_impl(tg_ctx* ctx, const PassList& pl, void* d_items, void* d_tmp,
     TG_CUDA(ctx, cudaMemsetAsync(hist, 0, hist_words * 4, ctx->stream));
     TG_CUDA(ctx, cudaMemsetAsync(status, 0, status_bytes, ctx->stream));
 
-    TG_LAUNCH_T(ctx, TG_K_RADIX_HIST, radix_hist_kernel<WORDS>, ctx->sm_count * 2, 512, pl.npass * RADIX * 4, (const Item*)d_items, n, pl, hist);
+    bool plain_u64 = WORDS == 1 && pl.npass == 8;
+    for (int p = 0; p < pl.npass && plain_u64; ++p) plain_u64 = pl.word[p] == 0 && pl.shift[p] == 8 * p;
+    if (plain_u64)
+        TG_LAUNCH_T(ctx, TG_K_RADIX_HIST, radix_hist_u64_kernel, ctx->sm_count * 2, 512, 0, (const u64*)d_items, n, pl.flip, hist);
+    else
+        TG_LAUNCH_T(ctx, TG_K_RADIX_HIST, radix_hist_kernel<WORDS>, ctx->sm_count * 2, 512, pl.npass * RADIX * 4, (const Item*)d_items, n, pl, hist);
     TG_LAUNCH(ctx, scan_hist_kernel, 1, RADIX, 0, hist, gbase, skip, pl.npass, (u32)n);
     u32* h_skip = (u32*)ctx->pinned;
     TG_CUDA(ctx, cudaMemcpyAsync(h_skip, skip, pl.npass * 4, cudaMemcpyDeviceToHost, ctx->stream));

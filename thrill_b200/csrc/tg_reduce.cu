@@ -61,12 +61,18 @@ __device__ __forceinline__ void op_apply(int op, u64* slot_val, u64 val, bool cl
 
 __device__ __forceinline__ u64 key_hash(u64 key) { return hash128to64_dev(0, key); }
 
-// ---- pre phase: per-CTA shared-memory tables ----------------------------------------------------------------------
+// ---- pre phase: per-CTA private tables ------------------------------------------------------------------------
+// 64-bit shared-memory atomics (u64/f64 add, min, max) are CAS spin loops on sm_100 (SASS ATOMS.CAST.SPIN.64),
+// which collapse under the contention of the Zipf head; global-memory 64-bit reductions are native
+// (RED.E.ADD.F64 at the L2).  So every CTA owns a PRIVATE open-addressing table in global memory, small enough
+// that all tables stay L2 resident (296 x 128 KB = 38 MB of the 126 MB L2): the hot keys are reduced with
+// native L2 atomics on CTA-private addresses (no cross-SM contention on a hot address), the table is frozen once
+// 3/4 full and misses are passed through as partial aggregates of their own; the table is emitted at the end
+// (FlushAll, reduce_probing_hash_table.hpp:484-488).
 constexpr int PRE_THREADS = 1024;
-constexpr int PRE_SLOTS = 8192;                  // 64 KB keys + 64 KB values
-constexpr int PRE_MAXPROBE = 8;
-constexpr int PRE_CHUNK = PRE_THREADS * 4;       // records between fill checks
-constexpr int PRE_SMEM = PRE_SLOTS * 16 + 64;
+constexpr int PRE_CTAS_PER_SM = 2;
+constexpr u32 PRE_SLOTS = 8192;                  // 16-byte slots: 128 KB per CTA
+constexpr int PRE_MAXPROBE = 4;
 
 // append one item to the global output (warp-aggregated cursor bump)
 __device__ __forceinline__ void emit_item(ulonglong2* __restrict__ out, u64* cursor, u64 key, u64 val, bool has) {
@@ -79,66 +85,64 @@ __device__ __forceinline__ void emit_item(ulonglong2* __restrict__ out, u64* cur
     if (has) out[base + __popc(m & lanemask_lt())] = make_ulonglong2(key, val);
 }
 
-__global__ void __launch_bounds__(PRE_THREADS, 1)
-preagg_kernel(const ulonglong2* __restrict__ in, u64 n, int op, ulonglong2* __restrict__ out, u64* __restrict__ cursor,
-              u64* __restrict__ zero_slot /* [0]=flag, [1]=value */) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    u64* keys = (u64*)smem;
-    u64* vals = keys + PRE_SLOTS;
-    u32* fill = (u32*)(vals + PRE_SLOTS);
-    const u64 ident = op_identity(op);
-    for (int i = threadIdx.x; i < PRE_SLOTS; i += PRE_THREADS) { keys[i] = 0; vals[i] = ident; }
-    if (threadIdx.x == 0) *fill = 0;
-    __syncthreads();
+__device__ __forceinline__ u64 ld_cg_u64(const u64* p) {
+    u64 v;
+    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 
-    const u64 per_cta = (n + gridDim.x - 1) / gridDim.x;
+__global__ void __launch_bounds__(PRE_THREADS, PRE_CTAS_PER_SM)
+preagg_kernel(const ulonglong2* __restrict__ in, u64 n, int op, ulonglong2* __restrict__ tables /* [grid][PRE_SLOTS], pre-set to (0, identity) */,
+              ulonglong2* __restrict__ out, u64* __restrict__ cursor, u64* __restrict__ zero_slot /* [0]=flag, [1]=value */) {
+    __shared__ u32 fill;
+    ulonglong2* tab = tables + (size_t)blockIdx.x * PRE_SLOTS;
+    if (threadIdx.x == 0) fill = 0;
+    __syncthreads();
+    const u64 per_cta = (((n + gridDim.x - 1) / gridDim.x) + PRE_THREADS - 1) / PRE_THREADS * PRE_THREADS;
     const u64 lo = per_cta * blockIdx.x;
     const u64 hi = lo + per_cta < n ? lo + per_cta : n;
-    for (u64 base = lo; base < hi; base += PRE_CHUNK) {
-#pragma unroll
-        for (int j = 0; j < PRE_CHUNK / PRE_THREADS; ++j) {
-            u64 i = base + (u64)j * PRE_THREADS + threadIdx.x;
-            bool valid = i < hi;
-            ulonglong2 kv = valid ? in[i] : make_ulonglong2(0, 0);
-            bool spill = false;
-            if (valid) {
-                if (kv.x == 0) {
-                    // Key() == 0: reduced in a side slot, never probed (reduce_probing_hash_table.hpp:195-218)
-                    u64 prev = atomicCAS(&zero_slot[0], 0ull, 1ull);
-                    op_apply(op, &zero_slot[1], kv.y, prev == 0);
-                }
-                else {
-                    u32 slot = (u32)(key_hash(kv.x) >> 32) & (PRE_SLOTS - 1);
-                    spill = true;
+    for (u64 base = lo; base < hi; base += PRE_THREADS) {
+        u64 i = base + threadIdx.x;
+        bool valid = i < hi;
+        ulonglong2 kv = valid ? in[i] : make_ulonglong2(0, 0);
+        bool spill = false;
+        if (valid) {
+            if (kv.x == 0) {
+                // Key() == 0: reduced in a side slot, never probed (reduce_probing_hash_table.hpp:195-218)
+                u64 prev = atomicCAS(&zero_slot[0], 0ull, 1ull);
+                op_apply(op, &zero_slot[1], kv.y, prev == 0);
+            }
+            else {
+                u32 slot = (u32)(key_hash(kv.x) >> 32) & (PRE_SLOTS - 1);
+                const bool frozen = *(volatile u32*)&fill > PRE_SLOTS * 3 / 4;
+                spill = true;
 #pragma unroll 1
-                    for (int pr = 0; pr < PRE_MAXPROBE; ++pr) {
-                        u64 prev = atomicCAS(&keys[slot], 0ull, kv.x);
-                        if (prev == 0 || prev == kv.x) {
-                            if (prev == 0) atomicAdd(fill, 1u);
-                            op_apply(op, &vals[slot], kv.y, prev == 0);
-                            spill = false;
-                            break;
-                        }
-                        slot = (slot + 1) & (PRE_SLOTS - 1);
+                for (int pr = 0; pr < PRE_MAXPROBE; ++pr) {
+                    u64 k = ld_cg_u64(&tab[slot].x);
+                    if (k == 0) {
+                        if (frozen) break;
+                        k = atomicCAS(&tab[slot].x, 0ull, kv.x);
+                        if (k == 0) atomicAdd(&fill, 1u);
                     }
+                    if (k == 0 || k == kv.x) {
+                        op_apply(op, &tab[slot].y, kv.y, k == 0);
+                        spill = false;
+                        break;
+                    }
+                    slot = (slot + 1) & (PRE_SLOTS - 1);
                 }
             }
-            // probe limit hit: pass the record through unreduced (a legal partial aggregate)
-            emit_item(out, cursor, kv.x, kv.y, spill);
         }
-        __syncthreads();
-        const bool last = base + PRE_CHUNK >= hi;
-        if (*fill > PRE_SLOTS * 3 / 4 || last) {
-            // FlushPartition (reduce_probing_hash_table.hpp:443-482): emit every used slot, reset the table
-            for (int i = threadIdx.x; i < PRE_SLOTS; i += PRE_THREADS) {
-                u64 k = keys[i];
-                emit_item(out, cursor, k, vals[i], k != 0);
-                keys[i] = 0; vals[i] = ident;
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) *fill = 0;
-        }
-        __syncthreads();
+        // table miss: pass the record through unreduced (a legal partial aggregate)
+        emit_item(out, cursor, kv.x, kv.y, spill);
+    }
+    // FlushAll: every reduction of this CTA must have landed in the L2 before the table is read back
+    __threadfence();
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < PRE_SLOTS; i += PRE_THREADS) {
+        u64 k = ld_cg_u64(&tab[i].x);
+        u64 v = ld_cg_u64(&tab[i].y);
+        emit_item(out, cursor, k, v, k != 0);
     }
 }
 
@@ -222,19 +226,25 @@ int read_cursor(tg_ctx* ctx, const ReduceScratch& sc, u64* out) {
     return TG_OK;
 }
 
-// pre phase: n records -> m partial aggregates in d_pre (capacity n + 1)
+// pre phase: n records -> m partial aggregates in d_pre (capacity n + grid*PRE_SLOTS + 1)
+size_t preagg_out_capacity(tg_ctx* ctx, u64 n) { return (size_t)n + (size_t)ctx->sm_count * PRE_CTAS_PER_SM * PRE_SLOTS + 2; }
+
 int run_preagg(tg_ctx* ctx, int op, const void* d_in, u64 n, void* d_pre, u64* out_m) {
     ReduceScratch sc;
     TG_TRY(get_scratch(ctx, op, &sc));
-    static bool attr_set = false;
-    if (!attr_set) {
-        TG_CUDA(ctx, cudaFuncSetAttribute(preagg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PRE_SMEM));
-        attr_set = true;
-    }
     if (n) {
-        u64 ctas = (n + PRE_CHUNK - 1) / PRE_CHUNK;
-        int grid = ctas < (u64)ctx->sm_count ? (int)ctas : ctx->sm_count;
-        TG_LAUNCH_T(ctx, TG_K_PREAGG, preagg_kernel, grid, PRE_THREADS, PRE_SMEM, (const ulonglong2*)d_in, n, op, (ulonglong2*)d_pre, sc.cursor, sc.zero_slot);
+        u64 ctas = (n + PRE_THREADS * 8 - 1) / (PRE_THREADS * 8);
+        int max_grid = ctx->sm_count * PRE_CTAS_PER_SM;
+        int grid = ctas < (u64)max_grid ? (int)ctas : max_grid;
+        ulonglong2* tables;
+        TG_TRY(tg_ws_get(ctx, WS_AUX2, (size_t)max_grid * PRE_SLOTS * 16, (void**)&tables));
+        if (op_identity_is_zero(op)) TG_CUDA(ctx, cudaMemsetAsync(tables, 0, (size_t)grid * PRE_SLOTS * 16, ctx->stream));
+        else {
+            u64 ident = (op == TG_OP_MIN_U64) ? ~0ull : (op == TG_OP_MIN_F64) ? 0x7FF0000000000000ull : 0xFFF0000000000000ull;
+            TG_LAUNCH(ctx, table_init_kernel, ctx->sm_count * 4, 512, 0, tables, (u64)grid * PRE_SLOTS, ident);
+        }
+        TG_LAUNCH_T(ctx, TG_K_PREAGG, preagg_kernel, grid, PRE_THREADS, 0, (const ulonglong2*)d_in, n, op, tables,
+                    (ulonglong2*)d_pre, sc.cursor, sc.zero_slot);
     }
     // the zero key's partial aggregate travels as one more item
     TG_LAUNCH(ctx, compact_kernel, 1, 32, 0, (const ulonglong2*)nullptr, (u64)0, (ulonglong2*)d_pre, sc.cursor, sc.zero_slot);
@@ -274,7 +284,7 @@ int tg_hash_aggregate(tg_ctx* ctx, const tg_kv_desc* desc, const void* d_in, siz
     TG_CUDA(ctx, cudaSetDevice(ctx->device));
     // pre phase into scratch, post phase into d_out
     void* d_pre;
-    TG_TRY(tg_ws_get(ctx, WS_AUX, (n + 2) * 16, &d_pre));
+    TG_TRY(tg_ws_get(ctx, WS_AUX, preagg_out_capacity(ctx, n) * 16, &d_pre));
     u64 m = 0;
     TG_TRY(run_preagg(ctx, (int)desc->op, d_in, n, d_pre, &m));
     u64 distinct = 0;
@@ -306,7 +316,7 @@ int tg_reduce_by_key(tg_ctx* ctx, const tg_kv_desc* desc, const void* d_in, size
     const int p = ctx->nranks, me = ctx->rank;
     // pre phase (ReducePrePhase, StartPreOp..StopPreOp: api/reduce_by_key.hpp:142-168)
     void* d_pre;
-    TG_TRY(tg_ws_get(ctx, WS_AUX, (n_local + 2) * 16, &d_pre));
+    TG_TRY(tg_ws_get(ctx, WS_AUX, preagg_out_capacity(ctx, n_local) * 16, &d_pre));
     u64 m = 0;
     TG_TRY(run_preagg(ctx, op, d_in, n_local, d_pre, &m));
     const void* d_post_in = d_pre;

@@ -403,6 +403,155 @@ int sort_multi_impl(tg_ctx* ctx, const tg_key_desc* desc, const KeyView& kv, voi
     return TG_OK;
 }
 
+
+// ---- records with payload (TeraSort: Record{uint8 key[10]; uint8 value[90]}, examples/terasort/terasort.cpp:31-42) ----
+// Sorted through 16-byte tuples {key bytes (<= 12, zero padded), u32 position}: build (read s, write 16), LSB radix
+// sort of the tuples (stable, so equal keys keep input order), one gather pass of the s-byte records.
+__global__ void make_tuples_kernel(const unsigned char* __restrict__ rec, u32 n, u32 item_bytes, u32 key_off, u32 key_bytes,
+                                   ulonglong2* __restrict__ tuples) {
+    u32 stride = gridDim.x * blockDim.x;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned char* r = rec + (size_t)i * item_bytes + key_off;
+        u64 w0 = 0, w1 = 0;
+        for (u32 j = 0; j < key_bytes && j < 8; ++j) w0 |= (u64)r[j] << (8 * j);
+        for (u32 j = 8; j < key_bytes; ++j) w1 |= (u64)r[j] << (8 * (j - 8));
+        w1 |= (u64)i << 32;                                  // bytes 12..15: position of the record
+        tuples[i] = make_ulonglong2(w0, w1);
+    }
+}
+
+// out[j] = rec[tuples[j].position]; item_bytes is a multiple of 4: one warp moves a record with coalesced 4-byte words
+__global__ void gather_records_kernel(const unsigned char* __restrict__ rec, const ulonglong2* __restrict__ tuples, u32 n,
+                                      u32 item_bytes, unsigned char* __restrict__ out) {
+    const u32 words = item_bytes / 4;
+    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const u32 lane = lane_id();
+    for (u32 j = warp; j < n; j += nwarps) {
+        u32 src = (u32)(tuples[j].y >> 32);
+        const u32* s4 = (const u32*)(rec + (size_t)src * item_bytes);
+        u32* d4 = (u32*)(out + (size_t)j * item_bytes);
+        for (u32 w = lane; w < words; w += 32) d4[w] = s4[w];
+    }
+}
+
+int sort_records_impl(tg_ctx* ctx, const tg_key_desc* desc, void* d_in, size_t n_local, uint64_t rng_seed,
+                      void** out_dptr, size_t* out_n) {
+    const u32 rb = desc->item_bytes;
+    if (rb % 4 || desc->key_kind != TG_KEY_BYTES_BE || desc->key_bytes > 12 || desc->descending)
+        return tg_set_error(ctx, TG_ERR_ARG, "sort: records need item_bytes %% 4 == 0 and an ascending byte-string key of <= 12 bytes");
+    if (n_local >= (1u << 30)) return tg_set_error(ctx, TG_ERR_TOO_LARGE, "sort: n_local=%zu", n_local);
+    const int p = ctx->nranks, me = ctx->rank;
+    tg_key_desc tdesc = { 16, 0, desc->key_bytes, TG_KEY_BYTES_BE, 0, 1 };
+    KeyView tkv = { 0, desc->key_bytes, TG_KEY_BYTES_BE, 0 };
+    ulonglong2* d_tup;
+    void* d_tmp;
+    TG_TRY(tg_ws_get(ctx, WS_AUX, (n_local + 1) * 16, (void**)&d_tup));
+    TG_TRY(tg_ws_get(ctx, WS_SORT_TMP, (n_local + 1) * 16, &d_tmp));
+    if (n_local)
+        TG_LAUNCH(ctx, make_tuples_kernel, ctx->sm_count * 8, 256, 0, (const unsigned char*)d_in, (u32)n_local, rb, desc->key_offset, desc->key_bytes, d_tup);
+
+    if (p == 1) {
+        TG_TRY(tg_radix_sort_items(ctx, &tdesc, d_tup, d_tmp, n_local));
+        unsigned char* d_out;
+        TG_TRY(tg_ws_get(ctx, WS_OUT, (n_local + 1) * (size_t)rb, (void**)&d_out));
+        if (n_local) TG_LAUNCH(ctx, gather_records_kernel, ctx->sm_count * 8, 256, 0, (const unsigned char*)d_in, d_tup, (u32)n_local, rb, d_out);
+        *out_dptr = d_out;
+        *out_n = n_local;
+        return TG_OK;
+    }
+
+    u64* h = (u64*)ctx->pinned;
+    u64* d_ctl;
+    TG_TRY(tg_ws_get(ctx, WS_MISC, 1 << 16, (void**)&d_ctl));
+    h[0] = n_local;
+    TG_CUDA(ctx, cudaMemcpyAsync(d_ctl, h, 8, cudaMemcpyHostToDevice, ctx->stream));
+    TG_NCCL(ctx, ncclAllGather(d_ctl, d_ctl + 8, 1, ncclUint64, ctx->comm, ctx->stream));
+    TG_CUDA(ctx, cudaMemcpyAsync(h, d_ctl + 8, 8 * p, cudaMemcpyDeviceToHost, ctx->stream));
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<u64> n_of(p);
+    u64 total = 0, prefix = 0;
+    for (int r = 0; r < p; ++r) { n_of[r] = h[r]; if (r < me) prefix += h[r]; total += h[r]; }
+    if (total == 0) { *out_dptr = nullptr; *out_n = 0; return TG_OK; }
+    std::vector<u32> ns_of(p);
+    u32 max_s = 1;
+    for (int r = 0; r < p; ++r) {
+        u64 want = n_of[r] ? tg_sample_size(n_of[r]) : 0;
+        ns_of[r] = (u32)(want < n_of[r] ? want : n_of[r]);
+        if (ns_of[r] > max_s) max_s = ns_of[r];
+    }
+    CanonIdx* d_samp;
+    TG_TRY(tg_ws_get(ctx, WS_SAMPLES, (size_t)(p + 1) * max_s * sizeof(CanonIdx) + 4096, (void**)&d_samp));
+    CanonIdx* d_mine = d_samp + (size_t)p * max_s;
+    if (ns_of[me])
+        TG_LAUNCH(ctx, draw_samples_kernel<2>, (ns_of[me] + 255) / 256, 256, 0, (const ulonglong2*)d_tup, (u64)n_local, prefix,
+                  rng_seed * 0x9E3779B97F4A7C15ull + (u64)me * 0x100000000ull, ns_of[me], tkv, (ulonglong2*)nullptr, d_mine);
+    TG_NCCL(ctx, ncclAllGather(d_mine, d_samp, (size_t)max_s * sizeof(CanonIdx), ncclUint8, ctx->comm, ctx->stream));
+    std::vector<CanonIdx> all((size_t)p * max_s);
+    TG_CUDA(ctx, cudaMemcpyAsync(all.data(), d_samp, all.size() * sizeof(CanonIdx), cudaMemcpyDeviceToHost, ctx->stream));
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<CanonIdx> samples, spl;
+    for (int r = 0; r < p; ++r)
+        for (u32 i = 0; i < ns_of[r]; ++i) samples.push_back(all[(size_t)r * max_s + i]);
+    pick_splitters(samples, (uint32_t)p, &spl);
+    const u32 nspl = (u32)spl.size();
+    CanonIdx* d_spl = d_samp;
+    u32* d_tie = (u32*)(d_ctl + 1024);
+    u64* d_bnd = d_ctl + 2048;
+    TG_CUDA(ctx, cudaMemcpyAsync(d_spl, spl.data(), nspl * sizeof(CanonIdx), cudaMemcpyHostToDevice, ctx->stream));
+    TG_CUDA(ctx, cudaMemsetAsync(d_tie, 0, 4096, ctx->stream));
+    if (n_local && nspl)
+        TG_LAUNCH(ctx, tie_count_kernel<2>, ctx->sm_count * 4, 512, 0, (const ulonglong2*)d_tup, (u32)n_local, prefix, tkv, d_spl, nspl, d_tie);
+    TG_TRY(tg_radix_sort_items(ctx, &tdesc, d_tup, d_tmp, n_local));
+    if (nspl) TG_LAUNCH(ctx, boundaries_kernel<2>, (nspl + 63) / 64, 64, 0, (const ulonglong2*)d_tup, (u32)n_local, tkv, d_spl, nspl, d_tie, d_bnd);
+    TG_CUDA(ctx, cudaMemcpyAsync(h, d_bnd, 8 * nspl, cudaMemcpyDeviceToHost, ctx->stream));
+    // locally sorted records (the run this worker contributes)
+    unsigned char* d_sorted;
+    TG_TRY(tg_ws_get(ctx, WS_XCHG_SEND, (n_local + 1) * (size_t)rb, (void**)&d_sorted));
+    if (n_local) TG_LAUNCH(ctx, gather_records_kernel, ctx->sm_count * 8, 256, 0, (const unsigned char*)d_in, d_tup, (u32)n_local, rb, d_sorted);
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<u64> send_cnt(p), send_off(p + 1, 0);
+    {
+        u64 prev = 0;
+        for (int r = 0; r < p; ++r) {
+            u64 b = (r < p - 1) ? h[r] : n_local;
+            send_cnt[r] = b - prev;
+            prev = b;
+            send_off[r + 1] = send_off[r] + send_cnt[r];
+        }
+    }
+    for (int r = 0; r < p; ++r) h[r] = send_cnt[r];
+    TG_CUDA(ctx, cudaMemcpyAsync(d_ctl, h, 8 * p, cudaMemcpyHostToDevice, ctx->stream));
+    TG_NCCL(ctx, ncclAllGather(d_ctl, d_ctl + 64, p, ncclUint64, ctx->comm, ctx->stream));
+    TG_CUDA(ctx, cudaMemcpyAsync(h, d_ctl + 64, 8 * p * p, cudaMemcpyDeviceToHost, ctx->stream));
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<u64> recv_cnt(p), recv_off(p + 1, 0);
+    for (int r = 0; r < p; ++r) { recv_cnt[r] = h[(size_t)r * p + me]; recv_off[r + 1] = recv_off[r] + recv_cnt[r]; }
+    const u64 n_recv = recv_off[p];
+    if (n_recv >= (1u << 30)) return tg_set_error(ctx, TG_ERR_TOO_LARGE, "sort: received %llu records", n_recv);
+    unsigned char* d_recv;
+    TG_TRY(tg_ws_get(ctx, WS_XCHG_RECV, (n_recv + 1) * (size_t)rb, (void**)&d_recv));
+    TG_NCCL(ctx, ncclGroupStart());
+    for (int r = 0; r < p; ++r) {
+        if (send_cnt[r]) TG_NCCL(ctx, ncclSend(d_sorted + send_off[r] * rb, send_cnt[r] * rb, ncclUint8, r, ctx->comm, ctx->stream));
+        if (recv_cnt[r]) TG_NCCL(ctx, ncclRecv(d_recv + recv_off[r] * rb, recv_cnt[r] * rb, ncclUint8, r, ctx->comm, ctx->stream));
+    }
+    TG_NCCL(ctx, ncclGroupEnd());
+    // merge the received runs through their tuples, then gather
+    ulonglong2* d_rtup;
+    ulonglong2* d_mtup;
+    TG_TRY(tg_ws_get(ctx, WS_AUX, (n_recv + 1) * 16, (void**)&d_rtup));
+    TG_TRY(tg_ws_get(ctx, WS_AUX2, (n_recv + 1) * 16, (void**)&d_mtup));
+    TG_TRY(tg_ws_get(ctx, WS_SORT_TMP, (n_recv + 1) * 16, &d_tmp));
+    if (n_recv) TG_LAUNCH(ctx, make_tuples_kernel, ctx->sm_count * 8, 256, 0, (const unsigned char*)d_recv, (u32)n_recv, rb, desc->key_offset, desc->key_bytes, d_rtup);
+    TG_TRY(merge_runs_impl<2>(ctx, tkv, d_rtup, (const uint64_t*)recv_cnt.data(), (uint32_t)p, d_mtup, d_tmp));
+    unsigned char* d_out;
+    TG_TRY(tg_ws_get(ctx, WS_OUT, (n_recv + 1) * (size_t)rb, (void**)&d_out));
+    if (n_recv) TG_LAUNCH(ctx, gather_records_kernel, ctx->sm_count * 8, 256, 0, (const unsigned char*)d_recv, d_mtup, (u32)n_recv, rb, d_out);
+    *out_dptr = d_out;
+    *out_n = (size_t)n_recv;
+    return TG_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -505,9 +654,11 @@ int tg_kway_merge(tg_ctx* ctx, const tg_key_desc* desc, const void* d_runs, cons
 
 int tg_sort(tg_ctx* ctx, const tg_key_desc* desc, void* d_in, size_t n_local, uint64_t rng_seed, void** out_dptr, size_t* out_n) {
     KeyView kv;
-    if (!ctx || !out_dptr || !out_n || make_key_view(desc, &kv) != TG_OK || (desc->item_bytes != 8 && desc->item_bytes != 16))
+    if (!ctx || !out_dptr || !out_n || make_key_view(desc, &kv) != TG_OK)
         return tg_set_error(ctx, TG_ERR_ARG, "sort: unsupported descriptor");
     TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (desc->item_bytes != 8 && desc->item_bytes != 16)
+        return sort_records_impl(ctx, desc, d_in, n_local, rng_seed, out_dptr, out_n);
     if (ctx->nranks == 1) {
         // workers_algo = 1: zero splitters, everything lands in bucket 0 (api/sort.hpp:575-579): local sort only
         void* d_tmp;
@@ -517,6 +668,7 @@ int tg_sort(tg_ctx* ctx, const tg_key_desc* desc, void* d_in, size_t n_local, ui
         *out_n = n_local;
         return TG_OK;
     }
+    if (ctx->nranks > 16) return tg_set_error(ctx, TG_ERR_ARG, "sort: at most 16 ranks");
     return desc->item_bytes == 8 ? sort_multi_impl<1>(ctx, desc, kv, d_in, n_local, rng_seed, out_dptr, out_n)
                                  : sort_multi_impl<2>(ctx, desc, kv, d_in, n_local, rng_seed, out_dptr, out_n);
 }
