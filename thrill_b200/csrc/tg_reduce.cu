@@ -69,20 +69,49 @@ __device__ __forceinline__ u64 key_hash(u64 key) { return hash128to64_dev(0, key
 // native L2 atomics on CTA-private addresses (no cross-SM contention on a hot address), the table is frozen once
 // 3/4 full and misses are passed through as partial aggregates of their own; the table is emitted at the end
 // (FlushAll, reduce_probing_hash_table.hpp:484-488).
-constexpr int PRE_THREADS = 1024;
+constexpr int PRE_THREADS = 512;
 constexpr int PRE_CTAS_PER_SM = 2;
 constexpr u32 PRE_SLOTS = 8192;                  // 16-byte slots: 128 KB per CTA
 constexpr int PRE_MAXPROBE = 4;
 
-// append one item to the global output (warp-aggregated cursor bump)
-__device__ __forceinline__ void emit_item(ulonglong2* __restrict__ out, u64* cursor, u64 key, u64 val, bool has) {
-    u32 m = __ballot_sync(0xffffffffu, has);
-    if (!m) return;
-    u64 base = 0;
-    int leader = __ffs(m) - 1;
-    if ((int)lane_id() == leader) base = atomicAdd(cursor, (u64)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (has) out[base + __popc(m & lanemask_lt())] = make_ulonglong2(key, val);
+// append items to the global output: ONE atomic on the global cursor per CTA per call (a cursor bumped per
+// warp is a single hot L2 address: ~4M serialized atomics per 1.25e8 records, measured 3-4 ms).  All threads of
+// the CTA must call it; NITEMS items per thread; `scratch` = 34 u32 of shared memory.
+template <int NITEMS>
+__device__ __forceinline__ void emit_block(ulonglong2* __restrict__ out, u64* cursor, const u64 (&key)[NITEMS],
+                                           const u64 (&val)[NITEMS], const bool (&has)[NITEMS], u32* scratch) {
+    const u32 lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    u32 mine = 0;
+#pragma unroll
+    for (int i = 0; i < NITEMS; ++i) mine += has[i] ? 1u : 0u;
+    // exclusive scan of `mine` inside the warp
+    u32 incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) scratch[warp] = incl;
+    __syncthreads();
+    u64* base_slot = reinterpret_cast<u64*>(scratch + 32);      // 8-byte aligned: scratch is 8-byte aligned
+    if (warp == 0) {
+        u32 w = lane < nwarps ? scratch[lane] : 0;
+        u32 winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u32 v = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += v;
+        }
+        scratch[lane] = winc - w;                                // exclusive offsets of the warps
+        u32 total = __shfl_sync(0xffffffffu, winc, 31);
+        if (lane == 0) *base_slot = total ? atomicAdd(cursor, (u64)total) : 0ull;
+    }
+    __syncthreads();
+    u64 pos = *base_slot + scratch[warp] + (incl - mine);
+#pragma unroll
+    for (int i = 0; i < NITEMS; ++i)
+        if (has[i]) out[pos++] = make_ulonglong2(key[i], val[i]);
+    __syncthreads();                                             // scratch is reused by the next call
 }
 
 __device__ __forceinline__ u64 ld_cg_u64(const u64* p) {
@@ -91,59 +120,82 @@ __device__ __forceinline__ u64 ld_cg_u64(const u64* p) {
     return v;
 }
 
+constexpr int PRE_ITEMS = 4;       // records per thread between two output reservations
+
 __global__ void __launch_bounds__(PRE_THREADS, PRE_CTAS_PER_SM)
 preagg_kernel(const ulonglong2* __restrict__ in, u64 n, int op, ulonglong2* __restrict__ tables /* [grid][PRE_SLOTS], pre-set to (0, identity) */,
               ulonglong2* __restrict__ out, u64* __restrict__ cursor, u64* __restrict__ zero_slot /* [0]=flag, [1]=value */) {
     __shared__ u32 fill;
+    __shared__ __align__(8) u32 scratch[36];
     ulonglong2* tab = tables + (size_t)blockIdx.x * PRE_SLOTS;
     if (threadIdx.x == 0) fill = 0;
     __syncthreads();
-    const u64 per_cta = (((n + gridDim.x - 1) / gridDim.x) + PRE_THREADS - 1) / PRE_THREADS * PRE_THREADS;
+    constexpr u64 STEP = (u64)PRE_THREADS * PRE_ITEMS;
+    const u64 per_cta = (((n + gridDim.x - 1) / gridDim.x) + STEP - 1) / STEP * STEP;
     const u64 lo = per_cta * blockIdx.x;
     const u64 hi = lo + per_cta < n ? lo + per_cta : n;
-    for (u64 base = lo; base < hi; base += PRE_THREADS) {
-        u64 i = base + threadIdx.x;
-        bool valid = i < hi;
-        ulonglong2 kv = valid ? in[i] : make_ulonglong2(0, 0);
-        bool spill = false;
-        if (valid) {
-            if (kv.x == 0) {
+    for (u64 base = lo; base < hi; base += STEP) {
+        u64 key[PRE_ITEMS], val[PRE_ITEMS], first[PRE_ITEMS];
+        u32 slot0[PRE_ITEMS];
+        bool spill[PRE_ITEMS], valid[PRE_ITEMS];
+        const bool frozen = *(volatile u32*)&fill > PRE_SLOTS * 3 / 4;
+        // all first probes of the PRE_ITEMS records in flight together (independent L2 round trips)
+#pragma unroll
+        for (int j = 0; j < PRE_ITEMS; ++j) {
+            u64 i = base + (u64)j * PRE_THREADS + threadIdx.x;
+            valid[j] = i < hi;
+            ulonglong2 kv = valid[j] ? in[i] : make_ulonglong2(0, 0);
+            key[j] = kv.x; val[j] = kv.y;
+            slot0[j] = (u32)(key_hash(kv.x) >> 32) & (PRE_SLOTS - 1);
+        }
+#pragma unroll
+        for (int j = 0; j < PRE_ITEMS; ++j) first[j] = __ldcg(&tab[slot0[j]].x);
+#pragma unroll
+        for (int j = 0; j < PRE_ITEMS; ++j) {
+            spill[j] = false;
+            if (!valid[j]) continue;
+            if (key[j] == 0) {
                 // Key() == 0: reduced in a side slot, never probed (reduce_probing_hash_table.hpp:195-218)
                 u64 prev = atomicCAS(&zero_slot[0], 0ull, 1ull);
-                op_apply(op, &zero_slot[1], kv.y, prev == 0);
+                op_apply(op, &zero_slot[1], val[j], prev == 0);
+                continue;
             }
-            else {
-                u32 slot = (u32)(key_hash(kv.x) >> 32) & (PRE_SLOTS - 1);
-                const bool frozen = *(volatile u32*)&fill > PRE_SLOTS * 3 / 4;
-                spill = true;
+            u32 slot = slot0[j];
+            u64 k = first[j];
+            spill[j] = true;
 #pragma unroll 1
-                for (int pr = 0; pr < PRE_MAXPROBE; ++pr) {
-                    u64 k = ld_cg_u64(&tab[slot].x);
-                    if (k == 0) {
-                        if (frozen) break;
-                        k = atomicCAS(&tab[slot].x, 0ull, kv.x);
-                        if (k == 0) atomicAdd(&fill, 1u);
-                    }
-                    if (k == 0 || k == kv.x) {
-                        op_apply(op, &tab[slot].y, kv.y, k == 0);
-                        spill = false;
-                        break;
-                    }
-                    slot = (slot + 1) & (PRE_SLOTS - 1);
+            for (int pr = 0; pr < PRE_MAXPROBE; ++pr) {
+                if (pr) k = ld_cg_u64(&tab[slot].x);
+                if (k == 0) {
+                    if (frozen) break;
+                    k = atomicCAS(&tab[slot].x, 0ull, key[j]);
+                    if (k == 0) atomicAdd(&fill, 1u);
                 }
+                if (k == 0 || k == key[j]) {
+                    op_apply(op, &tab[slot].y, val[j], k == 0);
+                    spill[j] = false;
+                    break;
+                }
+                slot = (slot + 1) & (PRE_SLOTS - 1);
             }
         }
-        // table miss: pass the record through unreduced (a legal partial aggregate)
-        emit_item(out, cursor, kv.x, kv.y, spill);
+        // table misses pass through unreduced (legal partial aggregates)
+        emit_block<PRE_ITEMS>(out, cursor, key, val, spill, scratch);
     }
     // FlushAll: every reduction of this CTA must have landed in the L2 before the table is read back
     __threadfence();
     __syncthreads();
-    for (u32 i = threadIdx.x; i < PRE_SLOTS; i += PRE_THREADS) {
-        u64 k = ld_cg_u64(&tab[i].x);
-        u64 v = ld_cg_u64(&tab[i].y);
-        emit_item(out, cursor, k, v, k != 0);
+    constexpr int FL = PRE_SLOTS / PRE_THREADS;
+    u64 key[FL], val[FL];
+    bool has[FL];
+#pragma unroll
+    for (int j = 0; j < FL; ++j) {
+        u32 i = j * PRE_THREADS + threadIdx.x;
+        key[j] = ld_cg_u64(&tab[i].x);
+        val[j] = ld_cg_u64(&tab[i].y);
+        has[j] = key[j] != 0;
     }
+    emit_block<FL>(out, cursor, key, val, has, scratch);
 }
 
 // ---- post phase: open addressing in HBM ------------------------------------------------------------------------
@@ -180,14 +232,26 @@ aggregate_kernel(const ulonglong2* __restrict__ in, u64 n, int op, ulonglong2* _
 __global__ void __launch_bounds__(512)
 compact_kernel(const ulonglong2* __restrict__ tab, u64 cap, ulonglong2* __restrict__ out, u64* __restrict__ cursor,
                const u64* __restrict__ zero_slot) {
-    u64 stride = (u64)gridDim.x * blockDim.x;
-    u64 rounds = (cap + stride - 1) / stride;
+    __shared__ __align__(8) u32 scratch[36];
+    constexpr int CI = 8;
+    const u64 stride = (u64)gridDim.x * blockDim.x * CI;
+    const u64 rounds = (cap + stride - 1) / stride;
     for (u64 r = 0; r < rounds; ++r) {
-        u64 i = r * stride + (u64)blockIdx.x * blockDim.x + threadIdx.x;
-        ulonglong2 e = i < cap ? tab[i] : make_ulonglong2(0, 0);
-        emit_item(out, cursor, e.x, e.y, e.x != 0);
+        u64 key[CI], val[CI];
+        bool has[CI];
+#pragma unroll
+        for (int j = 0; j < CI; ++j) {
+            u64 i = r * stride + ((u64)blockIdx.x * CI + j) * blockDim.x + threadIdx.x;
+            ulonglong2 e = i < cap ? tab[i] : make_ulonglong2(0, 0);
+            key[j] = e.x; val[j] = e.y; has[j] = e.x != 0;
+        }
+        emit_block<CI>(out, cursor, key, val, has, scratch);
     }
-    if (blockIdx.x == 0 && threadIdx.x < 32) emit_item(out, cursor, 0ull, zero_slot[1], threadIdx.x == 0 && zero_slot[0] != 0);
+    if (blockIdx.x == 0) {
+        u64 key[1] = { 0 }, val[1] = { zero_slot[1] };
+        bool has[1] = { threadIdx.x == 0 && zero_slot[0] != 0 };
+        emit_block<1>(out, cursor, key, val, has, scratch);
+    }
 }
 
 // destination worker of an item: Hash128to64(0, key) % p  (core/reduce_functional.hpp:60-72)
