@@ -3,7 +3,7 @@ import ctypes as C, sys
 from thrill_b200 import capi
 c = capi.Ctx(0)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100000000
-d = c.alloc(n * 8); tmp = c.alloc(n * 8)
+d = c.alloc(n * 8 + (4 << 20)); tmp = c.alloc(n * 8 + (4 << 20))
 desc = capi.u64_desc()
 for i in range(6):
     c.ck(c.L.tg_gen_sort_uniform(c.h, d, 0, n, 42)); c.sync()

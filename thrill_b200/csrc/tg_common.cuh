@@ -30,6 +30,9 @@ struct tg_ctx {
     size_t ws_bytes[TG_NUM_WS] = { 0 };
     void* pinned = nullptr;                     // small pinned staging area (control-plane scalars)
     size_t pinned_bytes = 0;
+    // per-device kernel attributes already applied by this ctx (cudaFuncSetAttribute is per device, and one
+    // process may drive several GPUs: Thrill runs its workers as threads): kernel -> resident CTAs per SM
+    std::map<const void*, int> kernel_cfg;
     // optional per-kernel-class timing (tg_profile_*)
     bool profile = false;
     struct ProfEv { int cls; cudaEvent_t a, b; };

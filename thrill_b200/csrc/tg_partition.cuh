@@ -122,7 +122,7 @@ static __global__ void scan_hist_kernel(const u32* __restrict__ ghist, u32* __re
 template <int WORDS, int THREADS, int MINB, int RANK, class DigitFn>
 __global__ void __launch_bounds__(THREADS, MINB)
 partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename ItemT<WORDS>::type* __restrict__ out,
-                 u32 n, const DigitFn fn_param, const u32* __restrict__ gbase, u32* __restrict__ status) {
+                 u32 n, const DigitFn fn_param, const u32* __restrict__ gbase, u32* __restrict__ status, int dbg) {
     typedef typename ItemT<WORDS>::type Item;
     typedef SweepCfg<WORDS, THREADS> C;
     constexpr int ITEMS = C::ITEMS, TILE = C::TILE, NWARPS = C::NWARPS;
@@ -205,7 +205,16 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
         // ---- stable rank inside the warp: ballots group equal digits, the group leader bumps the counter
         unsigned short rank[ITEMS];
         unsigned char mydig[ITEMS];
-        if (full_tile) {
+        if (full_tile && (dbg & 2)) {
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) {
+                u32 d = fn(key[i], tile_base + wbase + i * 32 + lane);
+                if (DigitFn::kStoreDigit) mydig[i] = (unsigned char)d;
+                rank[i] = (unsigned short)0;
+                if (lane == 0) whist_w[d] += 1;
+            }
+        }
+        else if (full_tile) {
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) {
                 u32 d = fn(key[i], tile_base + wbase + i * 32 + lane);
@@ -284,7 +293,7 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
         // ---- decoupled look-back (threads 0..RADIX-1, one digit each, LB predecessors per round trip)
         if (tid < RADIX) {
             u32 excl = 0;
-            if (t > 0) {
+            if (t > 0 && !(dbg & 1)) {
                 int look = (int)t - 1;
                 bool done = false;
                 while (!done) {
@@ -362,12 +371,19 @@ inline u32 num_tiles_for(size_t n) {
     return (u32)((n + tile - 1) / tile);
 }
 
+// timing experiments only (results are wrong when set): bit0 = skip the look-back wait, bit1 = skip ranking
+inline int debug_flags() {
+    static int f = -1;
+    if (f < 0) { const char* e = getenv("TG_DEBUG_FLAGS"); f = e ? atoi(e) : 0; }
+    return f;
+}
+
 inline int rank_mode() {
     static int m = -1;
     if (m < 0) {
         const char* e = getenv("TG_RANK_MODE");
-        m = e ? atoi(e) : 0;
-        if (m < 0 || m > 2) m = 0;
+        m = e ? atoi(e) : 2;
+        if (m < 0 || m > 2) m = 2;
     }
     return m;
 }
@@ -377,18 +393,21 @@ int launch_partition_v(tg_ctx* ctx, const void* in, void* out, u32 n, const Digi
     typedef typename ItemT<WORDS>::type Item;
     typedef SweepCfg<WORDS, THREADS> C;
     auto kern = partition_kernel<WORDS, THREADS, MINB, RANK, DigitFn>;
-    static int ctas_per_sm = 0;          // one per template instantiation
-    if (!ctas_per_sm) {
+    int ctas_per_sm = 0;
+    auto it = ctx->kernel_cfg.find((const void*)kern);
+    if (it != ctx->kernel_cfg.end()) ctas_per_sm = it->second;
+    else {
         TG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         // the look-back needs every CTA of the grid resident: size the grid from the real occupancy
         TG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, THREADS, C::SMEM));
         if (ctas_per_sm < 1) return tg_set_error(ctx, TG_ERR_CUDA, "partition kernel does not fit on an SM");
         if (ctas_per_sm > MINB) ctas_per_sm = MINB;
+        ctx->kernel_cfg[(const void*)kern] = ctas_per_sm;
     }
     u32 num_tiles = (n + C::TILE - 1) / C::TILE;
     int grid = ctx->sm_count * ctas_per_sm;
     if (grid > (int)num_tiles) grid = (int)num_tiles;
-    TG_LAUNCH_T(ctx, TG_K_PARTITION, kern, grid, THREADS, C::SMEM, (const Item*)in, (Item*)out, n, fn, gbase, status);
+    TG_LAUNCH_T(ctx, TG_K_PARTITION, kern, grid, THREADS, C::SMEM, (const Item*)in, (Item*)out, n, fn, gbase, status, debug_flags());
     return TG_OK;
 }
 
