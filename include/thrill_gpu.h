@@ -99,11 +99,14 @@ int tg_timer_start(tg_ctx* ctx);
 int tg_timer_stop(tg_ctx* ctx, float* out_ms);      /* synchronises */
 /* kernels launched by this ctx since tg_init (bench.py's gpu_launches) */
 uint64_t tg_launch_count(const tg_ctx* ctx);
+/* how many local sorts on this ctx abandoned the prefix sort (top digits + finishing pass) for the plain LSD passes
+ * because a run of equal key prefixes was too long (heavy duplicates); see tg_radix_sort_local */
+uint64_t tg_prefix_sort_fallbacks(const tg_ctx* ctx);
 /* per-kernel-class device timing (CUDA events around every launch of the class while enabled):
  * bench.py's live roofline measurement.  tg_profile_get synchronises and returns the summed duration
  * and the number of launches of `kernel_class` since tg_profile_enable(ctx, 1). */
 enum { TG_K_RADIX_HIST = 0, TG_K_PARTITION = 1, TG_K_MERGE = 2, TG_K_PREAGG = 3, TG_K_AGGREGATE = 4,
-       TG_K_COMPACT = 5, TG_K_OTHER = 6, TG_K_NUM = 7 };
+       TG_K_COMPACT = 5, TG_K_OTHER = 6, TG_K_FIXUP = 7, TG_K_NUM = 8 };
 int tg_profile_enable(tg_ctx* ctx, int on);
 int tg_profile_get(tg_ctx* ctx, int kernel_class, float* out_total_ms, uint64_t* out_launches);
 /* page-locked host memory (what the BlockPool arenas should be for full PCIe bandwidth; the host shim

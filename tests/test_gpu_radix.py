@@ -109,3 +109,73 @@ def test_radix_full_size_properties(ctx):
     head = ctx.download(d, 4096 * 8, np.uint64)
     assert np.all(head[1:] >= head[:-1])
     ctx.free(d); ctx.free(tmp)
+
+
+# ---- prefix sort: top digits by LSD passes + one finishing pass (tg_radix_sort.cu prefix_fixup_kernel) -----------
+
+def test_prefix_sort_wide_keys_with_duplicates_stable(ctx):
+    """16-byte items, wide u64 keys drawn from a pool (groups of ~6 fully equal keys): the finishing pass ranks
+    equal keys by position, so the result is the stable sort — bit-exact with the oracle."""
+    from thrill_b200 import capi
+    n = 300000
+    rng = np.random.RandomState(11)
+    pool = rng.randint(0, 2**63 - 1, size=50000, dtype=np.int64).astype(np.uint64)
+    kv = np.zeros(n, dtype=O.KV)
+    kv["key"] = pool[rng.randint(0, len(pool), size=n)]
+    kv["val"] = np.arange(n)
+    before = ctx.L.tg_prefix_sort_fallbacks(ctx.h)
+    out = _sort_on_gpu(ctx, kv, capi.kv_key_desc()).view(O.KV)
+    assert ctx.L.tg_prefix_sort_fallbacks(ctx.h) == before          # the fast path handled it
+    ref = O.sort_items(kv, O.KV_DESC).view(O.KV)
+    assert np.array_equal(out, ref)
+
+
+def test_prefix_sort_falls_back_on_long_equal_prefix_runs(ctx):
+    """every distinct key 150 times (> the 64 items the finishing pass can see): the sort must notice and fall back
+    to the plain LSD passes; the next sorts skip the attempt (penalty) and stay correct."""
+    from thrill_b200 import capi
+    n = 300000
+    rng = np.random.RandomState(12)
+    pool = rng.randint(0, 2**63 - 1, size=2000, dtype=np.int64).astype(np.uint64)
+    keys = np.repeat(pool, 150)
+    rng.shuffle(keys)
+    before = ctx.L.tg_prefix_sort_fallbacks(ctx.h)
+    out = _sort_on_gpu(ctx, keys, capi.u64_desc()).view(np.uint64)
+    assert np.array_equal(out, np.sort(keys))
+    assert ctx.L.tg_prefix_sort_fallbacks(ctx.h) == before + 1
+    for _ in range(10):         # penalty window, then a fresh (failing) attempt: always the right answer
+        out = _sort_on_gpu(ctx, keys, capi.u64_desc()).view(np.uint64)
+        assert np.array_equal(out, np.sort(keys))
+    uni = O.gen_sort_uniform(3, 100000)
+    for _ in range(10):
+        assert np.array_equal(_sort_on_gpu(ctx, uni, capi.u64_desc()).view(np.uint64), np.sort(uni))
+
+
+@pytest.mark.parametrize("n", [70000, 1 << 20])
+def test_prefix_sort_groups_straddle_tiles(ctx, n):
+    """keys = 40-bit random prefix in the high bits with only 2^14 distinct prefixes -> groups of 4..64 items that
+    cross the finishing pass's 2048-item tiles; low bits random."""
+    from thrill_b200 import capi
+    rng = np.random.RandomState(n)
+    npre = max(n // 24, 1)
+    pre = rng.randint(0, 2**39, size=npre, dtype=np.int64).astype(np.uint64) << np.uint64(24)
+    keys = pre[rng.randint(0, npre, size=n)] | rng.randint(0, 1 << 24, size=n).astype(np.uint64)
+    out = _sort_on_gpu(ctx, keys, capi.u64_desc()).view(np.uint64)
+    assert np.array_equal(out, np.sort(keys))
+
+
+def test_prefix_sort_descending_and_big_endian(ctx):
+    from thrill_b200 import capi
+    keys = O.gen_sort_uniform(9, 400000)
+    out = _sort_on_gpu(ctx, keys, capi.u64_desc(descending=True)).view(np.uint64)
+    assert np.array_equal(out, np.sort(keys)[::-1])
+    n = 250000
+    rng = np.random.RandomState(5)
+    t = np.zeros((n, 16), dtype=np.uint8)
+    t[:, :10] = rng.randint(0, 256, size=(n, 10))
+    t[:, 12:16] = np.arange(n, dtype=np.uint32).view(np.uint8).reshape(n, 4)
+    t[1::2, :10] = t[0::2, :10]                         # every key twice: ties resolved by position (stable)
+    desc = capi.KeyDesc(16, 0, 10, capi.KEY_BYTES_BE, 0, 0)
+    out = _sort_on_gpu(ctx, t, desc).reshape(n, 16)
+    ref = O.sort_items(t, O.KeyDesc(16, 0, 10, O.KEY_BYTES_BE)).reshape(n, 16)
+    assert np.array_equal(out, ref)

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "libthrill_gpu.so")
 TG_OK = 0
 KEY_UINT_LE, KEY_BYTES_BE = 0, 1
 OP_SUM_F64, OP_SUM_U64, OP_MIN_U64, OP_MAX_U64, OP_MIN_F64, OP_MAX_F64, OP_FIRST = range(7)
-K_RADIX_HIST, K_PARTITION, K_MERGE, K_PREAGG, K_AGGREGATE, K_COMPACT, K_OTHER = range(7)
+K_RADIX_HIST, K_PARTITION, K_MERGE, K_PREAGG, K_AGGREGATE, K_COMPACT, K_OTHER, K_FIXUP = range(8)
 
 
 class KeyDesc(C.Structure):
@@ -64,6 +64,7 @@ SYMBOLS = [
     ("tg_timer_start", _i, [_vp]),
     ("tg_timer_stop", _i, [_vp, _P(C.c_float)]),
     ("tg_launch_count", _u64, [_vp]),
+    ("tg_prefix_sort_fallbacks", _u64, [_vp]),
     ("tg_profile_enable", _i, [_vp, _i]),
     ("tg_profile_get", _i, [_vp, _i, _P(C.c_float), _P(_u64)]),
     ("tg_host_alloc", _i, [_vp, _sz, _P(_vp)]),

@@ -33,6 +33,9 @@ struct tg_ctx {
     // per-device kernel attributes already applied by this ctx (cudaFuncSetAttribute is per device, and one
     // process may drive several GPUs: Thrill runs its workers as threads): kernel -> resident CTAs per SM
     std::map<const void*, int> kernel_cfg;
+    // prefix sort (tg_radix_sort.cu): sorts to skip after a failed attempt, and how often it fell back
+    int prefix_sort_penalty = 0;
+    uint64_t prefix_sort_fallbacks = 0;
     // optional per-kernel-class timing (tg_profile_*)
     bool profile = false;
     struct ProfEv { int cls; cudaEvent_t a, b; };

@@ -164,6 +164,7 @@ int tg_rank(const tg_ctx* ctx) { return ctx->rank; }
 int tg_nranks(const tg_ctx* ctx) { return ctx->nranks; }
 void* tg_stream(const tg_ctx* ctx) { return (void*)ctx->stream; }
 uint64_t tg_launch_count(const tg_ctx* ctx) { return ctx->launches; }
+uint64_t tg_prefix_sort_fallbacks(const tg_ctx* ctx) { return ctx->prefix_sort_fallbacks; }
 
 int tg_sync(tg_ctx* ctx) {
     TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

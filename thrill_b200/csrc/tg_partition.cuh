@@ -41,33 +41,60 @@ struct RadixDigit {
     }
 };
 
-// warp-wide "which lanes hold the same 8-bit digit": 8 ballots + bit ops.  (match.any.sync costs ~64 issue
-// cycles of the ADU pipe per warp instruction on sm_100 — measured 66 % ADU-bound in profiles/ r1a — the
-// ballot form runs on the ordinary ALU/vote path.)
-template <bool CHECK_VALID>
-__device__ __forceinline__ u32 match_digit(u32 d, bool valid) {
-    u32 peers = 0xffffffffu;
-#pragma unroll
-    for (int b = 0; b < RADIX_BITS; ++b) {
-        bool bit = (d >> b) & 1u;
-        u32 m = __ballot_sync(0xffffffffu, bit);
-        peers &= bit ? m : ~m;
-    }
-    if (CHECK_VALID) {
-        u32 m = __ballot_sync(0xffffffffu, valid);
-        peers &= valid ? m : ~m;
-    }
+// warp-wide "which lanes hold the same 8-bit digit": 8 ballots, each fixed up for the lane's own bit.
+// Written in PTX so that ptxas emits, per bit, one LOP3 with a predicate result, one VOTE and one predicated
+// NOT, and 3-input LOP3s for the final AND (the C++ form compiled to ~45 instructions per call, this one to 28;
+// match.any.sync costs ~64 issue cycles of the ADU pipe per warp on sm_100 — profiles/r1a).
+__device__ __forceinline__ u32 match_digit8(u32 d) {
+    u32 peers;
+    asm volatile(
+        "{\n"
+        ".reg .pred p0, p1, p2, p3, p4, p5, p6, p7;\n"
+        ".reg .b32 m0, m1, m2, m3, m4, m5, m6, m7, t;\n"
+        "and.b32 t, %1, 1;   setp.ne.u32 p0, t, 0;\n"
+        "and.b32 t, %1, 2;   setp.ne.u32 p1, t, 0;\n"
+        "and.b32 t, %1, 4;   setp.ne.u32 p2, t, 0;\n"
+        "and.b32 t, %1, 8;   setp.ne.u32 p3, t, 0;\n"
+        "and.b32 t, %1, 16;  setp.ne.u32 p4, t, 0;\n"
+        "and.b32 t, %1, 32;  setp.ne.u32 p5, t, 0;\n"
+        "and.b32 t, %1, 64;  setp.ne.u32 p6, t, 0;\n"
+        "and.b32 t, %1, 128; setp.ne.u32 p7, t, 0;\n"
+        "vote.sync.ballot.b32 m0, p0, 0xffffffff;\n"
+        "vote.sync.ballot.b32 m1, p1, 0xffffffff;\n"
+        "vote.sync.ballot.b32 m2, p2, 0xffffffff;\n"
+        "vote.sync.ballot.b32 m3, p3, 0xffffffff;\n"
+        "vote.sync.ballot.b32 m4, p4, 0xffffffff;\n"
+        "vote.sync.ballot.b32 m5, p5, 0xffffffff;\n"
+        "vote.sync.ballot.b32 m6, p6, 0xffffffff;\n"
+        "vote.sync.ballot.b32 m7, p7, 0xffffffff;\n"
+        "@!p0 not.b32 m0, m0;\n"
+        "@!p1 not.b32 m1, m1;\n"
+        "@!p2 not.b32 m2, m2;\n"
+        "@!p3 not.b32 m3, m3;\n"
+        "@!p4 not.b32 m4, m4;\n"
+        "@!p5 not.b32 m5, m5;\n"
+        "@!p6 not.b32 m6, m6;\n"
+        "@!p7 not.b32 m7, m7;\n"
+        "lop3.b32 t, m0, m1, m2, 0x80;\n"
+        "lop3.b32 t, t, m3, m4, 0x80;\n"
+        "lop3.b32 t, t, m5, m6, 0x80;\n"
+        "and.b32 %0, t, m7;\n"
+        "}\n"
+        : "=r"(peers)
+        : "r"(d));
     return peers;
 }
 
-template <int WORDS, int THREADS>
+// tile geometry of one launch configuration: THREADS threads, each owning IPT items of WORDS 8-byte words
+template <int WORDS, int THREADS, int IPT>
 struct SweepCfg {
     static constexpr int ITEM_BYTES = 8 * WORDS;
-    static constexpr int ITEMS = 16 / WORDS;                 // per thread: 128 bytes of items
+    static constexpr int ITEMS = IPT;
     static constexpr int TILE = THREADS * ITEMS;             // items per tile
-    static constexpr int TILE_BYTES = TILE * ITEM_BYTES;     // 64 KB at 512 threads
+    static constexpr int TILE_BYTES = TILE * ITEM_BYTES;
     static constexpr int NWARPS = THREADS / 32;
-    static constexpr int SMEM = 2 * TILE_BYTES + 2 * NWARPS * RADIX * 4 + 2 * RADIX * 4 + 64 + 16 + TILE + 256;
+    // 2 landing/exchange buffers | warp counters [NWARPS][RADIX] | goff [RADIX] | warp_tot [16] | mbar [2] | dig [TILE]
+    static constexpr int SMEM = 2 * TILE_BYTES + NWARPS * RADIX * 4 + RADIX * 4 + 64 + 16 + TILE + 256;
 };
 
 // per-bucket counts of one digit function (the pre-pass of a stand-alone partition)
@@ -119,14 +146,46 @@ static __global__ void scan_hist_kernel(const u32* __restrict__ ghist, u32* __re
     }
 }
 
-template <int WORDS, int THREADS, int MINB, int RANK, class DigitFn>
+__device__ __forceinline__ u32 lds_u32(u32 addr) {
+    u32 v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u32(u32 addr, u32 v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
+// stable rank of the warp's ITEMS rows inside the (warp, digit) groups.  Every lane reads its group's counter, the
+// lowest lane of the group bumps it (same warp, program order: the read precedes the write).  whist_w = shared
+// address of the warp's RADIX counters.  rank = position inside the group | digit << 16 (if STORE).
+template <bool FULL, bool STORE, int ITEMS, class Item, class DigitFn>
+__device__ __forceinline__ void rank_rows(const Item (&key)[ITEMS], u32 (&rank)[ITEMS], const DigitFn& fn, u32 whist_w,
+                                          u32 pos0, u32 tile_base, u32 tile_valid, u32 lt) {
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const u32 p = pos0 + i * 32;
+        u32 d = fn(key[i], tile_base + p);
+        if (!FULL && p >= tile_valid) d = RADIX - 1;
+        const u32 a = whist_w + d * 4;
+        const u32 old = lds_u32(a);
+        const u32 peers = match_digit8(d);
+        const u32 below = peers & lt;
+        if (below == 0) sts_u32(a, old + __popc(peers));
+        rank[i] = old + __popc(below);
+        if (STORE) rank[i] |= d << 16;
+        __syncwarp();
+    }
+}
+
+// One tile: rank -> per-digit counts (published for the chained scan) -> scatter into the exchange buffer while
+// the look-back loads are in flight -> resolve the look-back -> coalesced write-out.
+template <int WORDS, int THREADS, int IPT, int MINB, class DigitFn>
 __global__ void __launch_bounds__(THREADS, MINB)
 partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename ItemT<WORDS>::type* __restrict__ out,
-                 u32 n, const DigitFn fn_param, const u32* __restrict__ gbase, u32* __restrict__ status, int dbg) {
+                 u32 n, const DigitFn fn_param, const u32* __restrict__ gbase, u32* __restrict__ status) {
     typedef typename ItemT<WORDS>::type Item;
-    typedef SweepCfg<WORDS, THREADS> C;
+    typedef SweepCfg<WORDS, THREADS, IPT> C;
     constexpr int ITEMS = C::ITEMS, TILE = C::TILE, NWARPS = C::NWARPS;
     constexpr int LB = 8;       // look-back batch: predecessors fetched concurrently
+    static_assert(THREADS >= RADIX, "one thread per digit in the scan phases");
 
     // plain pointer arithmetic on the shared array keeps the shared address space (LDS/STS, 32-bit addresses)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -136,20 +195,15 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
     u32* const goff = whist + NWARPS * RADIX;                                    // [RADIX]
     u32* const warp_tot = goff + RADIX;                                          // [16]
     u64* const mbar = reinterpret_cast<u64*>(warp_tot + 16);                     // [2]
-    u32* const wmask = reinterpret_cast<u32*>(mbar + 2);                         // [NWARPS][RADIX] (RANK != 0)
-    unsigned char* const dig = reinterpret_cast<unsigned char*>(wmask + NWARPS * RADIX);   // [TILE], only if kStoreDigit
+    unsigned char* const dig = reinterpret_cast<unsigned char*>(mbar + 2);       // [TILE], only if kStoreDigit
 
     const DigitFn fn = fn_param;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 num_tiles = (n + TILE - 1) / TILE;
     const u32 lt = lanemask_lt();
     u32* const whist_w = whist + warp * RADIX;
-    u32* const wmask_w = wmask + warp * RADIX;
+    const u32 whist_w_a = smem_u32(whist_w);
     const u32 wbase = warp * 32 * ITEMS;
-    if (RANK != 0) {
-#pragma unroll
-        for (int i = 0; i < RADIX / 32; ++i) wmask_w[i * 32 + lane] = 0;
-    }
 
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
@@ -185,8 +239,11 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
 #pragma unroll
         for (int i = 0; i < RADIX / 32; ++i) whist_w[i * 32 + lane] = 0;
 
-        // ---- items to registers: warp w owns tile positions [w*32*ITEMS, (w+1)*32*ITEMS), round-striped
+        // ---- items to registers: warp w owns tile positions [w*32*ITEMS, (w+1)*32*ITEMS), round-striped.
+        // Positions past the end of a partial (= the last) tile get digit RADIX-1: the stable ranking puts them
+        // behind every valid item, so they fall off the end of the exchange buffer and are never written.
         Item key[ITEMS];
+        u32 rank[ITEMS];                 // rank inside the (warp, digit) group | digit << 16 (if kStoreDigit)
         if (full_tile) {
             mbar_wait(&mbar[cur], (it >> 1) & 1);
             const Item* src = buf + wbase + lane;
@@ -202,71 +259,23 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
         }
         __syncwarp();
 
-        // ---- stable rank inside the warp: ballots group equal digits, the group leader bumps the counter
-        unsigned short rank[ITEMS];
-        unsigned char mydig[ITEMS];
-        if (full_tile && (dbg & 2)) {
-#pragma unroll
-            for (int i = 0; i < ITEMS; ++i) {
-                u32 d = fn(key[i], tile_base + wbase + i * 32 + lane);
-                if (DigitFn::kStoreDigit) mydig[i] = (unsigned char)d;
-                rank[i] = (unsigned short)0;
-                if (lane == 0) whist_w[d] += 1;
-            }
-        }
-        else if (full_tile) {
-#pragma unroll
-            for (int i = 0; i < ITEMS; ++i) {
-                u32 d = fn(key[i], tile_base + wbase + i * 32 + lane);
-                if (DigitFn::kStoreDigit) mydig[i] = (unsigned char)d;
-                u32 peers;
-                if (RANK == 0 || (RANK == 2 && (i & 1))) peers = match_digit<false>(d, true);
-                else {
-                    // warp-private mask table: one native 32-bit shared-memory atomic per key instead of 8 ballots
-                    atomicOr(&wmask_w[d], 1u << lane);
-                    __syncwarp();
-                    peers = wmask_w[d];
-                    __syncwarp();
-                }
-                u32 below = peers & lt;
-                u32 old = 0;
-                if (below == 0) {                       // lowest lane of its group
-                    if (!(RANK == 0 || (RANK == 2 && (i & 1)))) wmask_w[d] = 0;
-                    old = whist_w[d];
-                    whist_w[d] = old + __popc(peers);
-                }
-                old = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1);
-                rank[i] = (unsigned short)(old + __popc(below));
-                __syncwarp();
-            }
-        }
-        else {
-#pragma unroll
-            for (int i = 0; i < ITEMS; ++i) {
-                u32 p = wbase + i * 32 + lane;
-                bool valid = p < tile_valid;
-                u32 d = valid ? fn(key[i], tile_base + p) : 0u;
-                if (DigitFn::kStoreDigit) mydig[i] = (unsigned char)d;
-                u32 peers = match_digit<true>(d, valid);
-                u32 below = peers & lt;
-                u32 old = 0;
-                if (below == 0 && valid) {
-                    old = whist_w[d];
-                    whist_w[d] = old + __popc(peers);
-                }
-                old = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1);
-                rank[i] = (unsigned short)(old + __popc(below));
-                __syncwarp();
-            }
-        }
+        // ---- stable rank inside the warp (partial tiles always carry the digit along: padding has none)
+        if (full_tile) rank_rows<true, DigitFn::kStoreDigit>(key, rank, fn, whist_w_a, wbase + lane, tile_base, tile_valid, lt);
+        else rank_rows<false, true>(key, rank, fn, whist_w_a, wbase + lane, tile_base, tile_valid, lt);
         __syncthreads();      // all items are in registers (buf is free), all warp counters final
 
-        // ---- per-digit tile count; publish PARTIAL as early as possible; tile-local digit starts
+        // ---- per-digit tile count; publish PARTIAL as early as possible; start the look-back loads
         u32 count = 0, my_start = 0;
+        u32 lbv[LB];
         if (tid < RADIX) {
 #pragma unroll
             for (int w = 0; w < NWARPS; ++w) count += whist[w * RADIX + tid];
-            st_relaxed_u32(&status[(size_t)t * RADIX + tid], count | (t == 0 ? FLAG_INCL : FLAG_PARTIAL));
+            u32 pub = count;
+            if (!full_tile && tid == RADIX - 1) pub -= (u32)TILE - tile_valid;      // padding is not data
+            st_relaxed_u32(&status[(size_t)t * RADIX + tid], pub | (t == 0 ? FLAG_INCL : FLAG_PARTIAL));
+#pragma unroll
+            for (int k = 0; k < LB; ++k)
+                lbv[k] = ((int)t - 1 - k >= 0) ? ld_relaxed_u32(&status[(size_t)(t - 1 - k) * RADIX + tid]) : FLAG_INCL;
             u32 incl = count;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -290,55 +299,73 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
         }
         __syncthreads();
 
-        // ---- decoupled look-back (threads 0..RADIX-1, one digit each, LB predecessors per round trip)
+        // ---- scatter registers -> digit-ordered exchange buffer (reuses the landing buffer)
+        if (full_tile && !DigitFn::kStoreDigit) {
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) {
+                u32 d = fn(key[i], 0);
+                buf[lds_u32(whist_w_a + d * 4) + rank[i]] = key[i];
+            }
+        }
+        else {
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) {
+                u32 d = rank[i] >> 16;
+                u32 q = lds_u32(whist_w_a + d * 4) + (rank[i] & 0xffffu);
+                buf[q] = key[i];
+                if (DigitFn::kStoreDigit) dig[q] = (unsigned char)d;
+            }
+        }
+
+        // ---- decoupled look-back (threads 0..RADIX-1, one digit each, LB predecessors per round trip; the first
+        // batch was requested before the scatter)
         if (tid < RADIX) {
             u32 excl = 0;
-            if (t > 0 && !(dbg & 1)) {
+            if (t > 0) {
                 int look = (int)t - 1;
                 bool done = false;
-                while (!done) {
-                    u32 v[LB];
-#pragma unroll
-                    for (int k = 0; k < LB; ++k)
-                        v[k] = (look - k >= 0) ? ld_relaxed_u32(&status[(size_t)(look - k) * RADIX + tid]) : FLAG_INCL;
+                while (true) {
                     bool stalled = false;
 #pragma unroll
                     for (int k = 0; k < LB; ++k) {
                         if (!done && !stalled) {
-                            if (v[k] & FLAG_INCL) { excl += v[k] & VALUE_MASK; done = true; }
-                            else if (v[k] & FLAG_PARTIAL) { excl += v[k] & VALUE_MASK; look--; }
+                            if (lbv[k] & FLAG_INCL) { excl += lbv[k] & VALUE_MASK; done = true; }
+                            else if (lbv[k] & FLAG_PARTIAL) { excl += lbv[k] & VALUE_MASK; look--; }
                             else stalled = true;
                         }
                     }
+                    if (done) break;
+#pragma unroll
+                    for (int k = 0; k < LB; ++k)
+                        lbv[k] = (look - k >= 0) ? ld_relaxed_u32(&status[(size_t)(look - k) * RADIX + tid]) : FLAG_INCL;
                 }
-                st_relaxed_u32(&status[(size_t)t * RADIX + tid], (excl + count) | FLAG_INCL);
+                u32 pub = count;
+                if (!full_tile && tid == RADIX - 1) pub -= (u32)TILE - tile_valid;
+                st_relaxed_u32(&status[(size_t)t * RADIX + tid], (excl + pub) | FLAG_INCL);
             }
             goff[tid] = gbase[tid] + excl - my_start;
-        }
-
-        // ---- scatter registers -> digit-ordered exchange buffer (reuses the landing buffer)
-#pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-            u32 p = wbase + i * 32 + lane;
-            if (full_tile || p < tile_valid) {
-                u32 d = DigitFn::kStoreDigit ? (u32)mydig[i] : fn(key[i], tile_base + p);
-                u32 q = whist_w[d] + rank[i];
-                buf[q] = key[i];
-                if (DigitFn::kStoreDigit) dig[q] = (unsigned char)d;
-            }
         }
         __syncthreads();
 
         // ---- coalesced write-out: consecutive threads write consecutive addresses inside a digit run
         {
-            Item* const outp = out + tid;
             const Item* const bufp = buf + tid;
+            if (full_tile) {
 #pragma unroll
-            for (int i = 0; i < ITEMS; ++i) {
-                if (full_tile || (u32)(i * THREADS + tid) < tile_valid) {
+                for (int i = 0; i < ITEMS; ++i) {
                     Item v = bufp[i * THREADS];
                     u32 d = DigitFn::kStoreDigit ? (u32)dig[i * THREADS + tid] : fn(v, 0);
-                    outp[goff[d] + i * THREADS] = v;
+                    out[goff[d] + (u32)(i * THREADS + tid)] = v;
+                }
+            }
+            else {
+#pragma unroll
+                for (int i = 0; i < ITEMS; ++i) {
+                    if ((u32)(i * THREADS + tid) < tile_valid) {
+                        Item v = bufp[i * THREADS];
+                        u32 d = DigitFn::kStoreDigit ? (u32)dig[i * THREADS + tid] : fn(v, 0);
+                        out[goff[d] + (u32)(i * THREADS + tid)] = v;
+                    }
                 }
             }
         }
@@ -353,46 +380,33 @@ __global__ void copy_items_kernel(const typename ItemT<WORDS>::type* __restrict_
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = in[i];
 }
 
-// launch configurations (threads per CTA, CTAs per SM); selected once per process, TG_SWEEP_CFG overrides
-struct SweepVariant { int threads, minb; };
-constexpr SweepVariant kSweepVariants[] = { { 512, 1 }, { 256, 2 }, { 256, 3 }, { 384, 2 } };
+// launch configurations (threads per CTA, 8-byte words per thread, CTAs per SM); TG_SWEEP_CFG overrides the default
+struct SweepVariant { int threads, wpt, minb; };
+constexpr SweepVariant kSweepVariants[] = { { 512, 16, 1 }, { 256, 16, 2 }, { 256, 16, 3 }, { 384, 16, 2 },
+                                            { 512, 8, 2 },  { 256, 8, 4 },  { 512, 8, 3 },  { 1024, 8, 1 } };
+constexpr int kNumSweepVariants = sizeof(kSweepVariants) / sizeof(kSweepVariants[0]);
 inline int sweep_cfg() {
     static int cfg = -1;
     if (cfg < 0) {
         const char* e = getenv("TG_SWEEP_CFG");
         cfg = e ? atoi(e) : 0;
-        if (cfg < 0 || cfg > 3) cfg = 0;
+        if (cfg < 0 || cfg >= kNumSweepVariants) cfg = 0;
     }
     return cfg;
 }
 template <int WORDS>
 inline u32 num_tiles_for(size_t n) {
-    u32 tile = (u32)kSweepVariants[sweep_cfg()].threads * (16 / WORDS);
+    const SweepVariant& v = kSweepVariants[sweep_cfg()];
+    u32 tile = (u32)v.threads * (u32)(v.wpt / WORDS);
     return (u32)((n + tile - 1) / tile);
 }
 
-// timing experiments only (results are wrong when set): bit0 = skip the look-back wait, bit1 = skip ranking
-inline int debug_flags() {
-    static int f = -1;
-    if (f < 0) { const char* e = getenv("TG_DEBUG_FLAGS"); f = e ? atoi(e) : 0; }
-    return f;
-}
-
-inline int rank_mode() {
-    static int m = -1;
-    if (m < 0) {
-        const char* e = getenv("TG_RANK_MODE");
-        m = e ? atoi(e) : 2;
-        if (m < 0 || m > 2) m = 2;
-    }
-    return m;
-}
-
-template <int WORDS, int THREADS, int MINB, int RANK, class DigitFn>
+template <int WORDS, int THREADS, int WPT, int MINB, class DigitFn>
 int launch_partition_v(tg_ctx* ctx, const void* in, void* out, u32 n, const DigitFn& fn, const u32* gbase, u32* status) {
     typedef typename ItemT<WORDS>::type Item;
-    typedef SweepCfg<WORDS, THREADS> C;
-    auto kern = partition_kernel<WORDS, THREADS, MINB, RANK, DigitFn>;
+    constexpr int IPT = WPT / WORDS;
+    typedef SweepCfg<WORDS, THREADS, IPT> C;
+    auto kern = partition_kernel<WORDS, THREADS, IPT, MINB, DigitFn>;
     int ctas_per_sm = 0;
     auto it = ctx->kernel_cfg.find((const void*)kern);
     if (it != ctx->kernel_cfg.end()) ctas_per_sm = it->second;
@@ -407,22 +421,22 @@ int launch_partition_v(tg_ctx* ctx, const void* in, void* out, u32 n, const Digi
     u32 num_tiles = (n + C::TILE - 1) / C::TILE;
     int grid = ctx->sm_count * ctas_per_sm;
     if (grid > (int)num_tiles) grid = (int)num_tiles;
-    TG_LAUNCH_T(ctx, TG_K_PARTITION, kern, grid, THREADS, C::SMEM, (const Item*)in, (Item*)out, n, fn, gbase, status, debug_flags());
+    TG_LAUNCH_T(ctx, TG_K_PARTITION, kern, grid, THREADS, C::SMEM, (const Item*)in, (Item*)out, n, fn, gbase, status);
     return TG_OK;
 }
 
 // launch one partition pass with precomputed global bases (status must be zeroed, num_tiles*RADIX words)
 template <int WORDS, class DigitFn>
 int launch_partition(tg_ctx* ctx, const void* in, void* out, u32 n, const DigitFn& fn, const u32* gbase, u32* status) {
-    const int rm = rank_mode();
     switch (sweep_cfg()) {
-    case 1: return launch_partition_v<WORDS, 256, 2, 0, DigitFn>(ctx, in, out, n, fn, gbase, status);
-    case 2: return launch_partition_v<WORDS, 256, 3, 0, DigitFn>(ctx, in, out, n, fn, gbase, status);
-    case 3: return launch_partition_v<WORDS, 384, 2, 0, DigitFn>(ctx, in, out, n, fn, gbase, status);
-    default:
-        if (rm == 1) return launch_partition_v<WORDS, 512, 1, 1, DigitFn>(ctx, in, out, n, fn, gbase, status);
-        if (rm == 2) return launch_partition_v<WORDS, 512, 1, 2, DigitFn>(ctx, in, out, n, fn, gbase, status);
-        return launch_partition_v<WORDS, 512, 1, 0, DigitFn>(ctx, in, out, n, fn, gbase, status);
+    case 1: return launch_partition_v<WORDS, 256, 16, 2, DigitFn>(ctx, in, out, n, fn, gbase, status);
+    case 2: return launch_partition_v<WORDS, 256, 16, 3, DigitFn>(ctx, in, out, n, fn, gbase, status);
+    case 3: return launch_partition_v<WORDS, 384, 16, 2, DigitFn>(ctx, in, out, n, fn, gbase, status);
+    case 4: return launch_partition_v<WORDS, 512, 8, 2, DigitFn>(ctx, in, out, n, fn, gbase, status);
+    case 5: return launch_partition_v<WORDS, 256, 8, 4, DigitFn>(ctx, in, out, n, fn, gbase, status);
+    case 6: return launch_partition_v<WORDS, 512, 8, 3, DigitFn>(ctx, in, out, n, fn, gbase, status);
+    case 7: return launch_partition_v<WORDS, 1024, 8, 1, DigitFn>(ctx, in, out, n, fn, gbase, status);
+    default: return launch_partition_v<WORDS, 512, 16, 1, DigitFn>(ctx, in, out, n, fn, gbase, status);
     }
 }
 

@@ -8,6 +8,7 @@
 // first.  Digit positions where every key has the same value are skipped (identity passes).
 // HBM traffic: n*s for the histogram + per executed pass n*s read + n*s write (s = item bytes).
 #include "tg_partition.cuh"
+#include "tg_keys.cuh"
 
 using namespace tgp;
 
@@ -122,6 +123,95 @@ __global__ void __launch_bounds__(512) radix_hist_u64_kernel(const u64* __restri
         if (sh[i]) atomicAdd(&ghist[i], sh[i]);
 }
 
+// ---- finishing pass of the prefix sort --------------------------------------------------------------------------
+// After stable LSD passes over the most significant digits only, the items are ordered by a key PREFIX; items that
+// share a prefix form short runs ("groups") that still have to be ordered by the rest of the key.  For n keys and a
+// prefix of >= log2(n)+4 well-spread bits nearly every group is a single item, so one read + one write finishes the
+// sort instead of one partition pass per remaining digit.  Every item looks at its neighbours in a shared-memory
+// tile (with a halo of FIX_H items on both sides); members of a group of more than one item rank themselves by
+// counting the group's smaller keys (ties by position: stable).  A group longer than FIX_H cannot be seen whole from
+// every member's tile: the kernel raises *fail and the caller falls back to the plain LSD sort.
+constexpr int FIX_H = 64;
+constexpr int FIX_THREADS = 256;
+constexpr int FIX_IPT = 8;
+constexpr int FIX_TILE = FIX_THREADS * FIX_IPT;
+
+struct PrefixMask {
+    u64 hi, lo;
+};
+
+template <bool PLAIN, class Item>
+__device__ __forceinline__ Canon fix_canon(const Item& v, const KeyView& kv) {
+    if (PLAIN) {
+        Canon c;
+        c.hi = 0;
+        c.lo = item_word(v, 0);
+        return c;
+    }
+    return canon_key(v, kv);
+}
+template <bool PLAIN>
+__device__ __forceinline__ bool same_prefix(const Canon& a, const Canon& b, const PrefixMask& m) {
+    if (PLAIN) return ((a.lo ^ b.lo) & m.lo) == 0;
+    return (((a.hi ^ b.hi) & m.hi) | ((a.lo ^ b.lo) & m.lo)) == 0;
+}
+
+template <int WORDS, bool PLAIN>
+__global__ void __launch_bounds__(FIX_THREADS) prefix_fixup_kernel(const typename ItemT<WORDS>::type* __restrict__ in,
+                                                                   typename ItemT<WORDS>::type* __restrict__ out, u32 n,
+                                                                   KeyView kv, PrefixMask pm, u32* __restrict__ fail) {
+    typedef typename ItemT<WORDS>::type Item;
+    __shared__ Item s[FIX_TILE + 2 * FIX_H];
+    const u32 tile0 = blockIdx.x * FIX_TILE;                 // first owned position
+    const long long first = (long long)tile0 - FIX_H;        // position of s[0]
+    for (int j = threadIdx.x; j < FIX_TILE + 2 * FIX_H; j += FIX_THREADS) {
+        long long g = first + j;
+        if (g >= 0 && g < (long long)n) s[j] = in[g];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < FIX_IPT; ++r) {
+        const int li = FIX_H + r * FIX_THREADS + threadIdx.x;
+        const u32 g = tile0 + r * FIX_THREADS + threadIdx.x;
+        if (g >= n) continue;
+        const Item me = s[li];
+        const Canon k = fix_canon<PLAIN>(me, kv);
+        const bool head = g == 0 || !same_prefix<PLAIN>(fix_canon<PLAIN>(s[li - 1], kv), k, pm);
+        const bool tail = g == n - 1 || !same_prefix<PLAIN>(fix_canon<PLAIN>(s[li + 1], kv), k, pm);
+        if (head && tail) {
+            out[g] = me;
+            continue;
+        }
+        // group bounds [lo, hi] in tile coordinates
+        int lo = li, hi = li;
+        bool bad = false;
+        if (!head) {
+            for (;;) {
+                --lo;
+                if (li - lo >= FIX_H) { bad = true; break; }
+                if (first + lo == 0 || !same_prefix<PLAIN>(fix_canon<PLAIN>(s[lo - 1], kv), k, pm)) break;
+            }
+        }
+        if (!tail && !bad) {
+            for (;;) {
+                ++hi;
+                if (hi - lo >= FIX_H) { bad = true; break; }
+                if (first + hi == (long long)n - 1 || !same_prefix<PLAIN>(fix_canon<PLAIN>(s[hi + 1], kv), k, pm)) break;
+            }
+        }
+        if (bad) {
+            *fail = 1;
+            continue;
+        }
+        u32 rank = 0;
+        for (int x = lo; x <= hi; ++x) {
+            const Canon c = fix_canon<PLAIN>(s[x], kv);
+            rank += (canon_less(c, k) || (x < li && canon_eq(c, k))) ? 1u : 0u;
+        }
+        out[g - (u32)(li - lo) + rank] = me;
+    }
+}
+
 // digit passes of a key descriptor over the item's little-endian u64 words, least significant first
 int build_pass_list(const tg_key_desc* d, PassList* pl) {
     if (d->item_bytes != 8 && d->item_bytes != 16) return TG_ERR_ARG;
@@ -136,18 +226,52 @@ int build_pass_list(const tg_key_desc* d, PassList* pl) {
     return TG_OK;
 }
 
+// prefix mask (canonical key space) of the digit passes >= pass0: pass j is the j-th least significant key byte
+PrefixMask prefix_mask(const tg_key_desc* d, int pass0) {
+    PrefixMask m = { 0, 0 };
+    const u32 kb = d->key_bytes;
+    if (d->key_kind == TG_KEY_UINT_LE) {
+        const u64 all = kb >= 8 ? ~0ull : ((1ull << (8 * kb)) - 1);
+        m.lo = pass0 >= 8 ? 0 : (all & ~((1ull << (8 * pass0)) - 1));
+    }
+    else {
+        const u32 top = kb - (u32)pass0;         // leading key bytes; the canonical form is left-aligned
+        m.hi = top >= 8 ? ~0ull : (top ? ~0ull << (8 * (8 - top)) : 0);
+        m.lo = top > 8 ? (top >= 16 ? ~0ull : ~0ull << (8 * (16 - top))) : 0;
+    }
+    return m;
+}
+
+// number of leading digits after which a group of equal prefixes is expected to be a single key
+// (well-spread keys): 2^(8K) >= 16 n
+int prefix_digits_for(size_t n) {
+    int bits = 4;
+    while (bits < 64 && ((size_t)1 << bits) < n * 16) ++bits;
+    return (bits + 7) / 8;
+}
+
+bool prefix_sort_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("TG_PREFIX_SORT"); on = e ? atoi(e) : 1; }
+    return on != 0;
+}
+
+// The sorted items end up in *result (= d_items or d_tmp); result == nullptr asks for them in d_items.
 template <int WORDS>
-int radix_sort_impl(tg_ctx* ctx, const PassList& pl, void* d_items, void* d_tmp, size_t n) {
+int radix_sort_impl(tg_ctx* ctx, const tg_key_desc* desc, const PassList& pl, void* d_items, void* d_tmp, size_t n,
+                    void** result) {
     typedef typename ItemT<WORDS>::type Item;
     const u32 num_tiles = num_tiles_for<WORDS>(n);
 
-    u32* hist;      // [npass][RADIX] counts | [npass][RADIX] bases | [npass] skip
-    size_t hist_words = (size_t)2 * pl.npass * RADIX + MAX_PASSES;
+    u32* hist;      // [npass][RADIX] counts | [npass][RADIX] bases | [npass] skip | fail flag
+    size_t hist_words = (size_t)2 * pl.npass * RADIX + MAX_PASSES + 4;
     TG_TRY(tg_ws_get(ctx, WS_SORT_HIST, hist_words * 4, (void**)&hist));
     u32* gbase = hist + (size_t)pl.npass * RADIX;
     u32* skip = gbase + (size_t)pl.npass * RADIX;
+    u32* fail = skip + MAX_PASSES;
     u32* status;
-    size_t status_bytes = (size_t)pl.npass * num_tiles * RADIX * 4;
+    const size_t pass_status_bytes = (size_t)num_tiles * RADIX * 4;
+    size_t status_bytes = (size_t)pl.npass * pass_status_bytes;
     TG_TRY(tg_ws_get(ctx, WS_SORT_STATUS, status_bytes, (void**)&status));
     TG_CUDA(ctx, cudaMemsetAsync(hist, 0, hist_words * 4, ctx->stream));
     TG_CUDA(ctx, cudaMemsetAsync(status, 0, status_bytes, ctx->stream));
@@ -163,35 +287,78 @@ int radix_sort_impl(tg_ctx* ctx, const PassList& pl, void* d_items, void* d_tmp,
     TG_CUDA(ctx, cudaMemcpyAsync(h_skip, skip, pl.npass * 4, cudaMemcpyDeviceToHost, ctx->stream));
     TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 
+    int active[MAX_PASSES], nactive = 0;      // digit positions where the keys differ, least significant first
+    for (int p = 0; p < pl.npass; ++p)
+        if (!h_skip[p]) active[nactive++] = p;
+
     void* src = d_items;
     void* dst = d_tmp;
-    for (int p = 0; p < pl.npass; ++p) {
-        if (h_skip[p]) continue;       // every key has the same digit here: the pass is the identity
+    auto run_pass = [&](int p) -> int {
         RadixDigit fn = { (int)pl.word[p], (int)pl.shift[p], pl.flip };
         TG_TRY((launch_partition<WORDS, RadixDigit>(ctx, src, dst, (u32)n, fn, gbase + (size_t)p * RADIX,
                                                     status + (size_t)p * num_tiles * RADIX)));
         void* t = src; src = dst; dst = t;
+        return TG_OK;
+    };
+
+    // ---- prefix sort: the K most significant active digits, then one finishing pass (see prefix_fixup_kernel)
+    const int K = prefix_digits_for(n);
+    bool done = false;
+    if (prefix_sort_enabled() && nactive >= K + 2 && ctx->prefix_sort_penalty == 0) {
+        for (int a = nactive - K; a < nactive; ++a) TG_TRY(run_pass(active[a]));
+        KeyView kv;
+        if (make_key_view(desc, &kv) != TG_OK) return tg_set_error(ctx, TG_ERR_ARG, "radix sort: unsupported key descriptor");
+        PrefixMask pm = prefix_mask(desc, active[nactive - K]);
+        const u32 grid = (u32)((n + FIX_TILE - 1) / FIX_TILE);
+        if (plain_u64 && !desc->descending)
+            TG_LAUNCH_T(ctx, TG_K_FIXUP, (prefix_fixup_kernel<WORDS, true>), grid, FIX_THREADS, 0, (const Item*)src, (Item*)dst, (u32)n, kv, pm, fail);
+        else
+            TG_LAUNCH_T(ctx, TG_K_FIXUP, (prefix_fixup_kernel<WORDS, false>), grid, FIX_THREADS, 0, (const Item*)src, (Item*)dst, (u32)n, kv, pm, fail);
+        u32* h_fail = (u32*)ctx->pinned;
+        TG_CUDA(ctx, cudaMemcpyAsync(h_fail, fail, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (*h_fail == 0) {
+            void* t = src; src = dst; dst = t;
+            done = true;
+        }
+        else {
+            // a group of equal prefixes was longer than the finishing pass can see (heavy duplicates / clustered
+            // keys): plain LSD over all active digits from the current permutation of the input; skip the attempt
+            // for the next few sorts on this ctx
+            ctx->prefix_sort_penalty = 8;
+            ctx->prefix_sort_fallbacks++;
+            for (int a = nactive - K; a < nactive; ++a)
+                TG_CUDA(ctx, cudaMemsetAsync((char*)status + (size_t)active[a] * pass_status_bytes, 0, pass_status_bytes, ctx->stream));
+        }
     }
-    if (src != d_items)
+    else if (ctx->prefix_sort_penalty > 0 && nactive >= K + 2) ctx->prefix_sort_penalty--;
+
+    if (!done)
+        for (int a = 0; a < nactive; ++a) TG_TRY(run_pass(active[a]));
+
+    if (result) *result = src;
+    else if (src != d_items)
         TG_LAUNCH(ctx, copy_items_kernel<WORDS>, ctx->sm_count * 8, 256, 0, (const Item*)src, (Item*)d_items, n);
     return TG_OK;
 }
 
 }  // namespace
 
-// used by the operators (tg_sample_sort.cu): result in d_items
-int tg_radix_sort_items(tg_ctx* ctx, const tg_key_desc* desc, void* d_items, void* d_tmp, size_t n) {
+// used by the operators (tg_sample_sort.cu): the sorted items are in *result (d_items or d_tmp), or in d_items if
+// result == nullptr
+int tg_radix_sort_items(tg_ctx* ctx, const tg_key_desc* desc, void* d_items, void* d_tmp, size_t n, void** result) {
+    if (result) *result = d_items;
     if (n >= (1u << 30)) return tg_set_error(ctx, TG_ERR_TOO_LARGE, "radix sort: n=%zu >= 2^30", n);
     if (((uintptr_t)d_items | (uintptr_t)d_tmp) & 15) return tg_set_error(ctx, TG_ERR_ARG, "buffers must be 16-byte aligned");
     PassList pl;
     if (build_pass_list(desc, &pl) != TG_OK) return tg_set_error(ctx, TG_ERR_ARG, "radix sort: unsupported key descriptor");
     if (n < 2) return TG_OK;
-    return desc->item_bytes == 8 ? radix_sort_impl<1>(ctx, pl, d_items, d_tmp, n)
-                                 : radix_sort_impl<2>(ctx, pl, d_items, d_tmp, n);
+    return desc->item_bytes == 8 ? radix_sort_impl<1>(ctx, desc, pl, d_items, d_tmp, n, result)
+                                 : radix_sort_impl<2>(ctx, desc, pl, d_items, d_tmp, n, result);
 }
 
 extern "C" int tg_radix_sort_local(tg_ctx* ctx, const tg_key_desc* desc, void* d_items, void* d_tmp, size_t n) {
     if (!ctx || !desc) return TG_ERR_ARG;
     TG_CUDA(ctx, cudaSetDevice(ctx->device));
-    return tg_radix_sort_items(ctx, desc, d_items, d_tmp, n);
+    return tg_radix_sort_items(ctx, desc, d_items, d_tmp, n, nullptr);
 }

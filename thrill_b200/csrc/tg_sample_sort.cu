@@ -16,82 +16,13 @@
 #include <cmath>
 
 #include "tg_partition.cuh"
+#include "tg_keys.cuh"
 
 using namespace tgp;
 
-int tg_radix_sort_items(tg_ctx* ctx, const tg_key_desc* desc, void* d_items, void* d_tmp, size_t n);
+int tg_radix_sort_items(tg_ctx* ctx, const tg_key_desc* desc, void* d_items, void* d_tmp, size_t n, void** result);
 
 namespace {
-
-// ---- canonical keys: (hi, lo) compared as unsigned 128-bit == the reference comparator's order ----------
-struct KeyView {
-    u32 off, bytes, kind, desc;
-};
-
-struct Canon {
-    u64 hi, lo;
-};
-struct CanonIdx {
-    u64 hi, lo, idx;
-};
-
-__host__ __device__ inline bool canon_less(const Canon& a, const Canon& b) {
-    return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo);
-}
-__host__ __device__ inline bool canon_eq(const Canon& a, const Canon& b) { return a.hi == b.hi && a.lo == b.lo; }
-// LessSampleIndex (api/sort.hpp:419-422) on canonical keys
-__host__ __device__ inline bool canonidx_less(const CanonIdx& a, const CanonIdx& b) {
-    if (a.hi != b.hi) return a.hi < b.hi;
-    if (a.lo != b.lo) return a.lo < b.lo;
-    return a.idx < b.idx;
-}
-
-// byte j of an item held as little-endian u64 words
-template <class Item>
-__device__ __forceinline__ u32 item_byte(const Item& v, u32 j) {
-    return (u32)(item_word(v, (int)(j >> 3)) >> (8 * (j & 7))) & 0xffu;
-}
-
-template <class Item>
-__device__ __forceinline__ Canon canon_key(const Item& v, const KeyView& kv) {
-    Canon c;
-    c.hi = 0; c.lo = 0;
-    if (kv.kind == TG_KEY_UINT_LE) {
-        if (kv.bytes == 8 && (kv.off & 7) == 0) c.lo = item_word(v, (int)(kv.off >> 3));
-        else
-            for (u32 j = 0; j < kv.bytes; ++j) c.lo |= (u64)item_byte(v, kv.off + j) << (8 * j);
-    }
-    else {
-        for (u32 j = 0; j < kv.bytes && j < 8; ++j) c.hi |= (u64)item_byte(v, kv.off + j) << (8 * (7 - j));
-        for (u32 j = 8; j < kv.bytes; ++j) c.lo |= (u64)item_byte(v, kv.off + j) << (8 * (15 - j));
-    }
-    if (kv.desc) { c.hi = ~c.hi; c.lo = ~c.lo; }
-    return c;
-}
-
-Canon canon_key_host(const unsigned char* item, const KeyView& kv) {
-    Canon c;
-    c.hi = 0; c.lo = 0;
-    if (kv.kind == TG_KEY_UINT_LE) {
-        for (u32 j = 0; j < kv.bytes; ++j) c.lo |= (u64)item[kv.off + j] << (8 * j);
-    }
-    else {
-        for (u32 j = 0; j < kv.bytes && j < 8; ++j) c.hi |= (u64)item[kv.off + j] << (8 * (7 - j));
-        for (u32 j = 8; j < kv.bytes; ++j) c.lo |= (u64)item[kv.off + j] << (8 * (15 - j));
-    }
-    if (kv.desc) { c.hi = ~c.hi; c.lo = ~c.lo; }
-    return c;
-}
-
-int make_key_view(const tg_key_desc* d, KeyView* kv) {
-    if (!d) return TG_ERR_ARG;
-    if (d->key_bytes == 0 || d->key_offset + d->key_bytes > d->item_bytes) return TG_ERR_ARG;
-    if (d->key_kind == TG_KEY_UINT_LE && d->key_bytes > 8) return TG_ERR_ARG;
-    if (d->key_kind == TG_KEY_BYTES_BE && d->key_bytes > 16) return TG_ERR_ARG;
-    if (d->key_kind != TG_KEY_UINT_LE && d->key_kind != TG_KEY_BYTES_BE) return TG_ERR_ARG;
-    kv->off = d->key_offset; kv->bytes = d->key_bytes; kv->kind = d->key_kind; kv->desc = d->descending;
-    return TG_OK;
-}
 
 // ---- classification by splitters: bucket = #splitters (key, idx) < (item key, item global index) ----
 // == TransmitItems' tree descent + EqualSampleGreaterIndex walk (api/sort.hpp:478-502); the padded
@@ -359,8 +290,9 @@ int sort_multi_impl(tg_ctx* ctx, const tg_key_desc* desc, const KeyView& kv, voi
         TG_LAUNCH(ctx, tie_count_kernel<WORDS>, ctx->sm_count * 4, 512, 0, (const Item*)d_in, (u32)n_local, prefix, kv, d_spl, nspl, d_tie);
     void* d_tmp;
     TG_TRY(tg_ws_get(ctx, WS_SORT_TMP, n_local * s, &d_tmp));
-    TG_TRY(tg_radix_sort_items(ctx, desc, d_in, d_tmp, n_local));
-    if (nspl) TG_LAUNCH(ctx, boundaries_kernel<WORDS>, (nspl + 63) / 64, 64, 0, (const Item*)d_in, (u32)n_local, kv, d_spl, nspl, d_tie, d_bnd);
+    void* d_sorted;      // d_in or d_tmp, whichever the last pass wrote
+    TG_TRY(tg_radix_sort_items(ctx, desc, d_in, d_tmp, n_local, &d_sorted));
+    if (nspl) TG_LAUNCH(ctx, boundaries_kernel<WORDS>, (nspl + 63) / 64, 64, 0, (const Item*)d_sorted, (u32)n_local, kv, d_spl, nspl, d_tie, d_bnd);
     TG_CUDA(ctx, cudaMemcpyAsync(h, d_bnd, 8 * nspl, cudaMemcpyDeviceToHost, ctx->stream));
     TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     std::vector<u64> send_cnt(p), send_off(p + 1, 0);
@@ -387,7 +319,7 @@ int sort_multi_impl(tg_ctx* ctx, const tg_key_desc* desc, const KeyView& kv, voi
     TG_TRY(tg_ws_get(ctx, WS_XCHG_RECV, (n_recv + 1) * s, (void**)&d_recv));
     TG_NCCL(ctx, ncclGroupStart());
     for (int r = 0; r < p; ++r) {
-        if (send_cnt[r]) TG_NCCL(ctx, ncclSend((const Item*)d_in + send_off[r], send_cnt[r] * s, ncclUint8, r, ctx->comm, ctx->stream));
+        if (send_cnt[r]) TG_NCCL(ctx, ncclSend((const Item*)d_sorted + send_off[r], send_cnt[r] * s, ncclUint8, r, ctx->comm, ctx->stream));
         if (recv_cnt[r]) TG_NCCL(ctx, ncclRecv(d_recv + recv_off[r], recv_cnt[r] * s, ncclUint8, r, ctx->comm, ctx->stream));
     }
     TG_NCCL(ctx, ncclGroupEnd());
@@ -395,8 +327,8 @@ int sort_multi_impl(tg_ctx* ctx, const tg_key_desc* desc, const KeyView& kv, voi
     // (7) merge the p received sorted runs (source order = worker order: stable)
     Item* d_out;
     TG_TRY(tg_ws_get(ctx, WS_OUT, (n_recv + 1) * s, (void**)&d_out));
-    void* d_mtmp;
-    TG_TRY(tg_ws_get(ctx, WS_SORT_TMP, (n_recv + 1) * s, &d_mtmp));
+    void* d_mtmp;        // (WS_SORT_TMP may still be the send buffer of the exchange)
+    TG_TRY(tg_ws_get(ctx, WS_AUX2, (n_recv + 1) * s, &d_mtmp));
     TG_TRY(merge_runs_impl<WORDS>(ctx, kv, d_recv, (const uint64_t*)recv_cnt.data(), (uint32_t)p, d_out, d_mtmp));
     *out_dptr = d_out;
     *out_n = (size_t)n_recv;
@@ -451,10 +383,11 @@ int sort_records_impl(tg_ctx* ctx, const tg_key_desc* desc, void* d_in, size_t n
         TG_LAUNCH(ctx, make_tuples_kernel, ctx->sm_count * 8, 256, 0, (const unsigned char*)d_in, (u32)n_local, rb, desc->key_offset, desc->key_bytes, d_tup);
 
     if (p == 1) {
-        TG_TRY(tg_radix_sort_items(ctx, &tdesc, d_tup, d_tmp, n_local));
+        void* d_stup;
+        TG_TRY(tg_radix_sort_items(ctx, &tdesc, d_tup, d_tmp, n_local, &d_stup));
         unsigned char* d_out;
         TG_TRY(tg_ws_get(ctx, WS_OUT, (n_local + 1) * (size_t)rb, (void**)&d_out));
-        if (n_local) TG_LAUNCH(ctx, gather_records_kernel, ctx->sm_count * 8, 256, 0, (const unsigned char*)d_in, d_tup, (u32)n_local, rb, d_out);
+        if (n_local) TG_LAUNCH(ctx, gather_records_kernel, ctx->sm_count * 8, 256, 0, (const unsigned char*)d_in, (const ulonglong2*)d_stup, (u32)n_local, rb, d_out);
         *out_dptr = d_out;
         *out_n = n_local;
         return TG_OK;
@@ -501,13 +434,14 @@ int sort_records_impl(tg_ctx* ctx, const tg_key_desc* desc, void* d_in, size_t n
     TG_CUDA(ctx, cudaMemsetAsync(d_tie, 0, 4096, ctx->stream));
     if (n_local && nspl)
         TG_LAUNCH(ctx, tie_count_kernel<2>, ctx->sm_count * 4, 512, 0, (const ulonglong2*)d_tup, (u32)n_local, prefix, tkv, d_spl, nspl, d_tie);
-    TG_TRY(tg_radix_sort_items(ctx, &tdesc, d_tup, d_tmp, n_local));
-    if (nspl) TG_LAUNCH(ctx, boundaries_kernel<2>, (nspl + 63) / 64, 64, 0, (const ulonglong2*)d_tup, (u32)n_local, tkv, d_spl, nspl, d_tie, d_bnd);
+    void* d_stup;
+    TG_TRY(tg_radix_sort_items(ctx, &tdesc, d_tup, d_tmp, n_local, &d_stup));
+    if (nspl) TG_LAUNCH(ctx, boundaries_kernel<2>, (nspl + 63) / 64, 64, 0, (const ulonglong2*)d_stup, (u32)n_local, tkv, d_spl, nspl, d_tie, d_bnd);
     TG_CUDA(ctx, cudaMemcpyAsync(h, d_bnd, 8 * nspl, cudaMemcpyDeviceToHost, ctx->stream));
     // locally sorted records (the run this worker contributes)
     unsigned char* d_sorted;
     TG_TRY(tg_ws_get(ctx, WS_XCHG_SEND, (n_local + 1) * (size_t)rb, (void**)&d_sorted));
-    if (n_local) TG_LAUNCH(ctx, gather_records_kernel, ctx->sm_count * 8, 256, 0, (const unsigned char*)d_in, d_tup, (u32)n_local, rb, d_sorted);
+    if (n_local) TG_LAUNCH(ctx, gather_records_kernel, ctx->sm_count * 8, 256, 0, (const unsigned char*)d_in, (const ulonglong2*)d_stup, (u32)n_local, rb, d_sorted);
     TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     std::vector<u64> send_cnt(p), send_off(p + 1, 0);
     {
@@ -663,8 +597,9 @@ int tg_sort(tg_ctx* ctx, const tg_key_desc* desc, void* d_in, size_t n_local, ui
         // workers_algo = 1: zero splitters, everything lands in bucket 0 (api/sort.hpp:575-579): local sort only
         void* d_tmp;
         TG_TRY(tg_ws_get(ctx, WS_SORT_TMP, n_local * desc->item_bytes, &d_tmp));
-        TG_TRY(tg_radix_sort_items(ctx, desc, d_in, d_tmp, n_local));
-        *out_dptr = d_in;
+        void* d_sorted;
+        TG_TRY(tg_radix_sort_items(ctx, desc, d_in, d_tmp, n_local, &d_sorted));
+        *out_dptr = d_sorted;        // d_in or the ctx-owned sort buffer
         *out_n = n_local;
         return TG_OK;
     }
