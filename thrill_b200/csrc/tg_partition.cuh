@@ -16,6 +16,13 @@
 
 namespace tgp {
 
+#ifndef TG_LB
+#define TG_LB 8
+#endif
+#ifndef TG_PF
+#define TG_PF 1
+#endif
+
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
 
@@ -158,7 +165,7 @@ __device__ __forceinline__ void sts_u32(u32 addr, u32 v) { asm volatile("st.shar
 // address of the warp's RADIX counters.  rank = position inside the group | digit << 16 (if STORE).
 template <bool FULL, bool STORE, int ITEMS, class Item, class DigitFn>
 __device__ __forceinline__ void rank_rows(const Item (&key)[ITEMS], u32 (&rank)[ITEMS], const DigitFn& fn, u32 whist_w,
-                                          u32 pos0, u32 tile_base, u32 tile_valid, u32 lt) {
+                                          u32 pos0, u32 tile_base, u32 tile_valid, u32 lt, bool nomatch = false) {
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
         const u32 p = pos0 + i * 32;
@@ -166,7 +173,7 @@ __device__ __forceinline__ void rank_rows(const Item (&key)[ITEMS], u32 (&rank)[
         if (!FULL && p >= tile_valid) d = RADIX - 1;
         const u32 a = whist_w + d * 4;
         const u32 old = lds_u32(a);
-        const u32 peers = match_digit8(d);
+        const u32 peers = nomatch ? (~lt & (lt << 1 | 1u)) : match_digit8(d);
         const u32 below = peers & lt;
         if (below == 0) sts_u32(a, old + __popc(peers));
         rank[i] = old + __popc(below);
@@ -177,14 +184,17 @@ __device__ __forceinline__ void rank_rows(const Item (&key)[ITEMS], u32 (&rank)[
 
 // One tile: rank -> per-digit counts (published for the chained scan) -> scatter into the exchange buffer while
 // the look-back loads are in flight -> resolve the look-back -> coalesced write-out.
-template <int WORDS, int THREADS, int IPT, int MINB, class DigitFn>
+template <int WORDS, int THREADS, int IPT, int MINB, class DigitFn, bool DBG = false>
 __global__ void __launch_bounds__(THREADS, MINB)
 partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename ItemT<WORDS>::type* __restrict__ out,
-                 u32 n, const DigitFn fn_param, const u32* __restrict__ gbase, u32* __restrict__ status) {
+                 u32 n, const DigitFn fn_param, const u32* __restrict__ gbase, u32* __restrict__ status, int dbg) {
+    // DBG instantiations (TG_SWEEP_DEBUG, timing experiments only, results are wrong): dbg bit0 = no look-back wait,
+    // bit1 = no matching, bit2 = linear instead of scattered write-out, bit3 = no write-out
     typedef typename ItemT<WORDS>::type Item;
     typedef SweepCfg<WORDS, THREADS, IPT> C;
     constexpr int ITEMS = C::ITEMS, TILE = C::TILE, NWARPS = C::NWARPS;
-    constexpr int LB = 8;       // look-back batch: predecessors fetched concurrently
+    constexpr int LB = TG_LB;   // look-back batch: predecessors fetched concurrently
+    constexpr bool PF = TG_PF != 0;      // request the first batch before the scatter
     static_assert(THREADS >= RADIX, "one thread per digit in the scan phases");
 
     // plain pointer arithmetic on the shared array keeps the shared address space (LDS/STS, 32-bit addresses)
@@ -260,22 +270,24 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
         __syncwarp();
 
         // ---- stable rank inside the warp (partial tiles always carry the digit along: padding has none)
-        if (full_tile) rank_rows<true, DigitFn::kStoreDigit>(key, rank, fn, whist_w_a, wbase + lane, tile_base, tile_valid, lt);
+        if (full_tile) rank_rows<true, DigitFn::kStoreDigit>(key, rank, fn, whist_w_a, wbase + lane, tile_base, tile_valid, lt, DBG && (dbg & 2));
         else rank_rows<false, true>(key, rank, fn, whist_w_a, wbase + lane, tile_base, tile_valid, lt);
         __syncthreads();      // all items are in registers (buf is free), all warp counters final
 
         // ---- per-digit tile count; publish PARTIAL as early as possible; start the look-back loads
         u32 count = 0, my_start = 0;
-        u32 lbv[LB];
+        u32 lbv[PF ? LB : 1];
         if (tid < RADIX) {
 #pragma unroll
             for (int w = 0; w < NWARPS; ++w) count += whist[w * RADIX + tid];
             u32 pub = count;
             if (!full_tile && tid == RADIX - 1) pub -= (u32)TILE - tile_valid;      // padding is not data
             st_relaxed_u32(&status[(size_t)t * RADIX + tid], pub | (t == 0 ? FLAG_INCL : FLAG_PARTIAL));
+            if (PF) {
 #pragma unroll
-            for (int k = 0; k < LB; ++k)
-                lbv[k] = ((int)t - 1 - k >= 0) ? ld_relaxed_u32(&status[(size_t)(t - 1 - k) * RADIX + tid]) : FLAG_INCL;
+                for (int k = 0; k < LB; ++k)
+                    lbv[PF ? k : 0] = ((int)t - 1 - k >= 0) ? ld_relaxed_u32(&status[(size_t)(t - 1 - k) * RADIX + tid]) : FLAG_INCL;
+            }
             u32 incl = count;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -321,23 +333,33 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
         // batch was requested before the scatter)
         if (tid < RADIX) {
             u32 excl = 0;
-            if (t > 0) {
+            if (t > 0 && !(DBG && (dbg & 1))) {
                 int look = (int)t - 1;
                 bool done = false;
+                u32 v[LB];
+                if (PF) {
+#pragma unroll
+                    for (int k = 0; k < LB; ++k) v[k] = lbv[PF ? k : 0];
+                }
+                else {
+#pragma unroll
+                    for (int k = 0; k < LB; ++k)
+                        v[k] = (look - k >= 0) ? ld_relaxed_u32(&status[(size_t)(look - k) * RADIX + tid]) : FLAG_INCL;
+                }
                 while (true) {
                     bool stalled = false;
 #pragma unroll
                     for (int k = 0; k < LB; ++k) {
                         if (!done && !stalled) {
-                            if (lbv[k] & FLAG_INCL) { excl += lbv[k] & VALUE_MASK; done = true; }
-                            else if (lbv[k] & FLAG_PARTIAL) { excl += lbv[k] & VALUE_MASK; look--; }
+                            if (v[k] & FLAG_INCL) { excl += v[k] & VALUE_MASK; done = true; }
+                            else if (v[k] & FLAG_PARTIAL) { excl += v[k] & VALUE_MASK; look--; }
                             else stalled = true;
                         }
                     }
                     if (done) break;
 #pragma unroll
                     for (int k = 0; k < LB; ++k)
-                        lbv[k] = (look - k >= 0) ? ld_relaxed_u32(&status[(size_t)(look - k) * RADIX + tid]) : FLAG_INCL;
+                        v[k] = (look - k >= 0) ? ld_relaxed_u32(&status[(size_t)(look - k) * RADIX + tid]) : FLAG_INCL;
                 }
                 u32 pub = count;
                 if (!full_tile && tid == RADIX - 1) pub -= (u32)TILE - tile_valid;
@@ -355,7 +377,9 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
                 for (int i = 0; i < ITEMS; ++i) {
                     Item v = bufp[i * THREADS];
                     u32 d = DigitFn::kStoreDigit ? (u32)dig[i * THREADS + tid] : fn(v, 0);
-                    out[goff[d] + (u32)(i * THREADS + tid)] = v;
+                    if (DBG && (dbg & 8)) continue;
+                    if (DBG && (dbg & 4)) out[tile_base + (u32)(i * THREADS + tid)] = v;
+                    else out[goff[d] + (u32)(i * THREADS + tid)] = v;
                 }
             }
             else {
@@ -401,12 +425,18 @@ inline u32 num_tiles_for(size_t n) {
     return (u32)((n + tile - 1) / tile);
 }
 
-template <int WORDS, int THREADS, int WPT, int MINB, class DigitFn>
+inline int sweep_debug() {
+    static int f = -1;
+    if (f < 0) { const char* e = getenv("TG_SWEEP_DEBUG"); f = e ? atoi(e) : 0; }
+    return f;
+}
+
+template <int WORDS, int THREADS, int WPT, int MINB, class DigitFn, bool DBG = false>
 int launch_partition_v(tg_ctx* ctx, const void* in, void* out, u32 n, const DigitFn& fn, const u32* gbase, u32* status) {
     typedef typename ItemT<WORDS>::type Item;
     constexpr int IPT = WPT / WORDS;
     typedef SweepCfg<WORDS, THREADS, IPT> C;
-    auto kern = partition_kernel<WORDS, THREADS, IPT, MINB, DigitFn>;
+    auto kern = partition_kernel<WORDS, THREADS, IPT, MINB, DigitFn, DBG>;
     int ctas_per_sm = 0;
     auto it = ctx->kernel_cfg.find((const void*)kern);
     if (it != ctx->kernel_cfg.end()) ctas_per_sm = it->second;
@@ -421,13 +451,25 @@ int launch_partition_v(tg_ctx* ctx, const void* in, void* out, u32 n, const Digi
     u32 num_tiles = (n + C::TILE - 1) / C::TILE;
     int grid = ctx->sm_count * ctas_per_sm;
     if (grid > (int)num_tiles) grid = (int)num_tiles;
-    TG_LAUNCH_T(ctx, TG_K_PARTITION, kern, grid, THREADS, C::SMEM, (const Item*)in, (Item*)out, n, fn, gbase, status);
+    TG_LAUNCH_T(ctx, TG_K_PARTITION, kern, grid, THREADS, C::SMEM, (const Item*)in, (Item*)out, n, fn, gbase, status, DBG ? sweep_debug() : 0);
     return TG_OK;
 }
 
 // launch one partition pass with precomputed global bases (status must be zeroed, num_tiles*RADIX words)
 template <int WORDS, class DigitFn>
 int launch_partition(tg_ctx* ctx, const void* in, void* out, u32 n, const DigitFn& fn, const u32* gbase, u32* status) {
+#ifdef TG_DBG_BUILD
+    if (sweep_debug()) {
+        switch (sweep_cfg()) {
+        case 1: return launch_partition_v<WORDS, 256, 16, 2, DigitFn, true>(ctx, in, out, n, fn, gbase, status);
+        case 2: return launch_partition_v<WORDS, 256, 16, 3, DigitFn, true>(ctx, in, out, n, fn, gbase, status);
+        case 3: return launch_partition_v<WORDS, 384, 16, 2, DigitFn, true>(ctx, in, out, n, fn, gbase, status);
+        case 4: return launch_partition_v<WORDS, 512, 8, 2, DigitFn, true>(ctx, in, out, n, fn, gbase, status);
+        case 6: return launch_partition_v<WORDS, 512, 8, 3, DigitFn, true>(ctx, in, out, n, fn, gbase, status);
+        default: return launch_partition_v<WORDS, 512, 16, 1, DigitFn, true>(ctx, in, out, n, fn, gbase, status);
+        }
+    }
+#endif
     switch (sweep_cfg()) {
     case 1: return launch_partition_v<WORDS, 256, 16, 2, DigitFn>(ctx, in, out, n, fn, gbase, status);
     case 2: return launch_partition_v<WORDS, 256, 16, 3, DigitFn>(ctx, in, out, n, fn, gbase, status);

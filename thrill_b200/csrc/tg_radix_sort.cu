@@ -156,59 +156,93 @@ __device__ __forceinline__ bool same_prefix(const Canon& a, const Canon& b, cons
     return (((a.hi ^ b.hi) & m.hi) | ((a.lo ^ b.lo) & m.lo)) == 0;
 }
 
+// the members of a group of more than one item: bounds by scanning the shared tile, rank by counting
+template <bool PLAIN, class Item>
+__device__ __noinline__ void fixup_group_member(const Item* s, int li, long long first, u32 n, const KeyView& kv,
+                                                const PrefixMask& pm, bool head, bool tail, Item* __restrict__ out,
+                                                u32* __restrict__ fail) {
+    const Item me = s[li];
+    const Canon k = fix_canon<PLAIN>(me, kv);
+    int lo = li, hi = li;
+    bool bad = false;
+    if (!head) {
+        for (;;) {
+            --lo;
+            if (li - lo >= FIX_H) { bad = true; break; }
+            if (first + lo == 0 || !same_prefix<PLAIN>(fix_canon<PLAIN>(s[lo - 1], kv), k, pm)) break;
+        }
+    }
+    if (!tail && !bad) {
+        for (;;) {
+            ++hi;
+            if (hi - lo >= FIX_H) { bad = true; break; }
+            if (first + hi == (long long)n - 1 || !same_prefix<PLAIN>(fix_canon<PLAIN>(s[hi + 1], kv), k, pm)) break;
+        }
+    }
+    if (bad) {
+        *fail = 1;
+        return;
+    }
+    u32 rank = 0;
+    for (int x = lo; x <= hi; ++x) {
+        const Canon c = fix_canon<PLAIN>(s[x], kv);
+        rank += (canon_less(c, k) || (x < li && canon_eq(c, k))) ? 1u : 0u;
+    }
+    out[(u32)(first + lo) + rank] = me;
+}
+
 template <int WORDS, bool PLAIN>
 __global__ void __launch_bounds__(FIX_THREADS) prefix_fixup_kernel(const typename ItemT<WORDS>::type* __restrict__ in,
                                                                    typename ItemT<WORDS>::type* __restrict__ out, u32 n,
                                                                    KeyView kv, PrefixMask pm, u32* __restrict__ fail) {
     typedef typename ItemT<WORDS>::type Item;
-    __shared__ Item s[FIX_TILE + 2 * FIX_H];
+    __shared__ __align__(16) Item s[FIX_TILE + 2 * FIX_H];
     const u32 tile0 = blockIdx.x * FIX_TILE;                 // first owned position
     const long long first = (long long)tile0 - FIX_H;        // position of s[0]
-    for (int j = threadIdx.x; j < FIX_TILE + 2 * FIX_H; j += FIX_THREADS) {
-        long long g = first + j;
-        if (g >= 0 && g < (long long)n) s[j] = in[g];
+    const bool interior = tile0 >= (u32)FIX_H && (size_t)tile0 + FIX_TILE + FIX_H <= n;
+    if (interior) {
+        // whole tile + halo in range: 16-byte loads (tile0 - FIX_H is a multiple of 64 items)
+        constexpr int VEC = (FIX_TILE + 2 * FIX_H) * (int)sizeof(Item) / 16;
+        const uint4* src = reinterpret_cast<const uint4*>(in + (tile0 - FIX_H));
+        uint4* dst = reinterpret_cast<uint4*>(s);
+#pragma unroll
+        for (int j = 0; j < (VEC + FIX_THREADS - 1) / FIX_THREADS; ++j) {
+            int q = j * FIX_THREADS + threadIdx.x;
+            if (q < VEC) dst[q] = src[q];
+        }
+    }
+    else {
+        for (int j = threadIdx.x; j < FIX_TILE + 2 * FIX_H; j += FIX_THREADS) {
+            long long g = first + j;
+            if (g >= 0 && g < (long long)n) s[j] = in[g];
+        }
     }
     __syncthreads();
+    if (interior) {
 #pragma unroll
-    for (int r = 0; r < FIX_IPT; ++r) {
-        const int li = FIX_H + r * FIX_THREADS + threadIdx.x;
-        const u32 g = tile0 + r * FIX_THREADS + threadIdx.x;
-        if (g >= n) continue;
-        const Item me = s[li];
-        const Canon k = fix_canon<PLAIN>(me, kv);
-        const bool head = g == 0 || !same_prefix<PLAIN>(fix_canon<PLAIN>(s[li - 1], kv), k, pm);
-        const bool tail = g == n - 1 || !same_prefix<PLAIN>(fix_canon<PLAIN>(s[li + 1], kv), k, pm);
-        if (head && tail) {
-            out[g] = me;
-            continue;
+        for (int r = 0; r < FIX_IPT; ++r) {
+            const int li = FIX_H + r * FIX_THREADS + threadIdx.x;
+            const Item me = s[li];
+            const Canon k = fix_canon<PLAIN>(me, kv);
+            const bool head = !same_prefix<PLAIN>(fix_canon<PLAIN>(s[li - 1], kv), k, pm);
+            const bool tail = !same_prefix<PLAIN>(fix_canon<PLAIN>(s[li + 1], kv), k, pm);
+            if (head && tail) out[tile0 + r * FIX_THREADS + threadIdx.x] = me;
+            else fixup_group_member<PLAIN>(s, li, first, n, kv, pm, head, tail, out, fail);
         }
-        // group bounds [lo, hi] in tile coordinates
-        int lo = li, hi = li;
-        bool bad = false;
-        if (!head) {
-            for (;;) {
-                --lo;
-                if (li - lo >= FIX_H) { bad = true; break; }
-                if (first + lo == 0 || !same_prefix<PLAIN>(fix_canon<PLAIN>(s[lo - 1], kv), k, pm)) break;
-            }
+    }
+    else {
+#pragma unroll 1
+        for (int r = 0; r < FIX_IPT; ++r) {
+            const int li = FIX_H + r * FIX_THREADS + threadIdx.x;
+            const u32 g = tile0 + r * FIX_THREADS + threadIdx.x;
+            if (g >= n) continue;
+            const Item me = s[li];
+            const Canon k = fix_canon<PLAIN>(me, kv);
+            const bool head = g == 0 || !same_prefix<PLAIN>(fix_canon<PLAIN>(s[li - 1], kv), k, pm);
+            const bool tail = g == n - 1 || !same_prefix<PLAIN>(fix_canon<PLAIN>(s[li + 1], kv), k, pm);
+            if (head && tail) out[g] = me;
+            else fixup_group_member<PLAIN>(s, li, first, n, kv, pm, head, tail, out, fail);
         }
-        if (!tail && !bad) {
-            for (;;) {
-                ++hi;
-                if (hi - lo >= FIX_H) { bad = true; break; }
-                if (first + hi == (long long)n - 1 || !same_prefix<PLAIN>(fix_canon<PLAIN>(s[hi + 1], kv), k, pm)) break;
-            }
-        }
-        if (bad) {
-            *fail = 1;
-            continue;
-        }
-        u32 rank = 0;
-        for (int x = lo; x <= hi; ++x) {
-            const Canon c = fix_canon<PLAIN>(s[x], kv);
-            rank += (canon_less(c, k) || (x < li && canon_eq(c, k))) ? 1u : 0u;
-        }
-        out[g - (u32)(li - lo) + rank] = me;
     }
 }
 
