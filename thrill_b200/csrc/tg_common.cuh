@@ -15,7 +15,7 @@
 typedef unsigned long long u64;
 typedef unsigned int u32;
 
-#define TG_NUM_WS 12
+#define TG_NUM_WS 17
 
 struct tg_ctx {
     int device = 0, rank = 0, nranks = 1;
@@ -30,11 +30,14 @@ struct tg_ctx {
     size_t ws_bytes[TG_NUM_WS] = { 0 };
     void* pinned = nullptr;                     // small pinned staging area (control-plane scalars)
     size_t pinned_bytes = 0;
+    void* pinned_list = nullptr;                // pinned staging of host-built tile lists (tg_pinned_list)
+    size_t pinned_list_bytes = 0;
     // per-device kernel attributes already applied by this ctx (cudaFuncSetAttribute is per device, and one
     // process may drive several GPUs: Thrill runs its workers as threads): kernel -> resident CTAs per SM
     std::map<const void*, int> kernel_cfg;
     // prefix sort (tg_radix_sort.cu): sorts to skip after a failed attempt, and how often it fell back
     int prefix_sort_penalty = 0;
+    int prefix_spec_penalty = 0;               // ... after the speculative fast path guessed the wrong top digit
     uint64_t prefix_sort_fallbacks = 0;
     // optional per-kernel-class timing (tg_profile_*)
     bool profile = false;
@@ -49,10 +52,13 @@ struct tg_ctx {
 
 // workspace slots
 enum { WS_SORT_TMP = 0, WS_SORT_STATUS = 1, WS_SORT_HIST = 2, WS_XCHG_SEND = 3, WS_XCHG_RECV = 4,
-       WS_MISC = 5, WS_TABLE = 6, WS_OUT = 7, WS_IN = 8, WS_AUX = 9, WS_AUX2 = 10, WS_SAMPLES = 11 };
+       WS_MISC = 5, WS_TABLE = 6, WS_OUT = 7, WS_IN = 8, WS_AUX = 9, WS_AUX2 = 10, WS_SAMPLES = 11,
+       WS_SEG_TILES = 12, WS_SEG_TABLES = 13, WS_SORT_STATUS2 = 14,
+       WS_SORT_HIST2 = 15, WS_SEG_TILES2 = 16 };
 
 int tg_set_error(tg_ctx* ctx, int status, const char* fmt, ...);
 int tg_ws_get(tg_ctx* ctx, int slot, size_t bytes, void** out);
+int tg_pinned_list(tg_ctx* ctx, size_t bytes, void** out);      // grown on demand, owned by the ctx
 
 #define TG_CUDA(ctx, call)                                                                         \
     do {                                                                                           \

@@ -13,6 +13,22 @@ int tg_set_error(tg_ctx* ctx, int status, const char* fmt, ...) {
     return status;
 }
 
+int tg_pinned_list(tg_ctx* ctx, size_t bytes, void** out) {
+    if (ctx->pinned_list_bytes < bytes) {
+        if (ctx->pinned_list) {
+            TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            TG_CUDA(ctx, cudaFreeHost(ctx->pinned_list));
+            ctx->pinned_list = nullptr;
+            ctx->pinned_list_bytes = 0;
+        }
+        size_t want = bytes + (bytes >> 2) + 4096;
+        TG_CUDA(ctx, cudaMallocHost(&ctx->pinned_list, want));
+        ctx->pinned_list_bytes = want;
+    }
+    *out = ctx->pinned_list;
+    return TG_OK;
+}
+
 int tg_ws_get(tg_ctx* ctx, int slot, size_t bytes, void** out) {
     if (bytes == 0) bytes = 256;
     if (ctx->ws_bytes[slot] < bytes) {
@@ -151,6 +167,7 @@ int tg_shutdown(tg_ctx* ctx) {
     for (int i = 0; i < TG_NUM_WS; ++i)
         if (ctx->ws[i]) cudaFree(ctx->ws[i]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->pinned_list) cudaFreeHost(ctx->pinned_list);
     for (auto& e : ctx->prof_events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);

@@ -182,12 +182,26 @@ __device__ __forceinline__ void rank_rows(const Item (&key)[ITEMS], u32 (&rank)[
     }
 }
 
+// Segmented operation: the input is a sequence of independent segments (e.g. the 256 buckets of a previous pass on
+// a more significant digit); every segment is partitioned on its own, with its own bases and its own chained scan.
+// The host lists the tiles in an order that interleaves the segments, so the tile a tile's scan depends on (the
+// previous tile of the same segment) was processed a whole wave of CTAs earlier: the look-back finds its inclusive
+// prefix with one load instead of waiting for tiles that are being processed at the same time.
+//   tiles[j] = { first item, items (<= TILE), status row, (segment << 20) | index of the tile inside its segment }
+//   status rows of one segment are consecutive; segbase[segment][RADIX] = output position of the segment's digit d.
+struct SegList {
+    const uint4* tiles;
+    const u32* segbase;
+    u32 num_tiles;
+};
+
 // One tile: rank -> per-digit counts (published for the chained scan) -> scatter into the exchange buffer while
 // the look-back loads are in flight -> resolve the look-back -> coalesced write-out.
-template <int WORDS, int THREADS, int IPT, int MINB, class DigitFn, bool DBG = false>
+template <int WORDS, int THREADS, int IPT, int MINB, class DigitFn, bool SEG, bool DBG = false>
 __global__ void __launch_bounds__(THREADS, MINB)
 partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename ItemT<WORDS>::type* __restrict__ out,
-                 u32 n, const DigitFn fn_param, const u32* __restrict__ gbase, u32* __restrict__ status, int dbg) {
+                 u32 n, const DigitFn fn_param, const u32* __restrict__ gbase, u32* __restrict__ status, const SegList sl,
+                 int dbg) {
     // DBG instantiations (TG_SWEEP_DEBUG, timing experiments only, results are wrong): dbg bit0 = no look-back wait,
     // bit1 = no matching, bit2 = linear instead of scattered write-out, bit3 = no write-out
     typedef typename ItemT<WORDS>::type Item;
@@ -209,11 +223,29 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
 
     const DigitFn fn = fn_param;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u32 num_tiles = (n + TILE - 1) / TILE;
+    const u32 num_tiles = SEG ? sl.num_tiles : (n + TILE - 1) / TILE;
     const u32 lt = lanemask_lt();
     u32* const whist_w = whist + warp * RADIX;
     const u32 whist_w_a = smem_u32(whist_w);
     const u32 wbase = warp * 32 * ITEMS;
+
+    // tile j: first item, items, status row, index inside its segment, segment
+    struct TileInfo { u32 start, len, row, idx, seg; };
+    auto tile_info = [&](u32 j) -> TileInfo {
+        TileInfo ti;
+        if (SEG) {
+            const uint4 d = __ldg(&sl.tiles[j]);
+            ti.start = d.x; ti.len = d.y; ti.row = d.z; ti.idx = d.w & 0xfffffu; ti.seg = d.w >> 20;
+        }
+        else {
+            ti.start = j * TILE;
+            ti.len = (n - ti.start < (u32)TILE) ? n - ti.start : (u32)TILE;
+            ti.row = j; ti.idx = j; ti.seg = 0;
+        }
+        return ti;
+    };
+    // a whole tile at a 16-byte aligned address is fetched by the TMA unit, anything else by ordinary loads
+    auto tma_ok = [&](const TileInfo& ti) -> bool { return ti.len == (u32)TILE && (((size_t)ti.start * sizeof(Item)) & 15) == 0; };
 
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
@@ -222,27 +254,34 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
     }
     __syncthreads();
 
-    u32 t = blockIdx.x;
-    if (tid == 0 && t < num_tiles && (size_t)(t + 1) * TILE <= n) {
-        mbar_expect_tx(&mbar[0], C::TILE_BYTES);
-        bulk_g2s(buf0, in + (size_t)t * TILE, C::TILE_BYTES, &mbar[0]);
+    u32 j = blockIdx.x;
+    if (j < num_tiles) {
+        const TileInfo t0 = tile_info(j);
+        if (tid == 0 && tma_ok(t0)) {
+            mbar_expect_tx(&mbar[0], C::TILE_BYTES);
+            bulk_g2s(buf0, in + t0.start, C::TILE_BYTES, &mbar[0]);
+        }
     }
+    u32 phase = 0;        // bit b: parity of the next completion of mbar[b]
 
-    for (u32 it = 0; t < num_tiles; t += gridDim.x, ++it) {
+    for (u32 it = 0; j < num_tiles; j += gridDim.x, ++it) {
         const int cur = it & 1;
         Item* const buf = cur ? buf1 : buf0;
         Item* const nbuf = cur ? buf0 : buf1;
-        const u32 tile_base = t * TILE;
-        const bool full_tile = (size_t)tile_base + TILE <= n;
-        const u32 tile_valid = full_tile ? (u32)TILE : n - tile_base;
+        const TileInfo ti = tile_info(j);
+        const u32 tile_base = ti.start;
+        const bool full_tile = ti.len == (u32)TILE;
+        const u32 tile_valid = ti.len;
+        const bool by_tma = tma_ok(ti);
+        const u32* const gb = SEG ? sl.segbase + (size_t)ti.seg * RADIX : gbase;
 
         // prefetch the CTA's next tile (TMA unit, async proxy) into the other buffer
-        {
-            u32 tn = t + gridDim.x;
-            if (tid == 0 && tn < num_tiles && (size_t)(tn + 1) * TILE <= n) {
+        if (tid == 0 && j + gridDim.x < num_tiles) {
+            const TileInfo tn = tile_info(j + gridDim.x);
+            if (tma_ok(tn)) {
                 fence_proxy_async();
                 mbar_expect_tx(&mbar[cur ^ 1], C::TILE_BYTES);
-                bulk_g2s(nbuf, in + (size_t)tn * TILE, C::TILE_BYTES, &mbar[cur ^ 1]);
+                bulk_g2s(nbuf, in + tn.start, C::TILE_BYTES, &mbar[cur ^ 1]);
             }
         }
         // zero this warp's private digit counters
@@ -250,13 +289,19 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
         for (int i = 0; i < RADIX / 32; ++i) whist_w[i * 32 + lane] = 0;
 
         // ---- items to registers: warp w owns tile positions [w*32*ITEMS, (w+1)*32*ITEMS), round-striped.
-        // Positions past the end of a partial (= the last) tile get digit RADIX-1: the stable ranking puts them
-        // behind every valid item, so they fall off the end of the exchange buffer and are never written.
+        // Positions past the end of a partial tile get digit RADIX-1: the stable ranking puts them behind every
+        // valid item, so they fall off the end of the exchange buffer and are never written.
         Item key[ITEMS];
         u32 rank[ITEMS];                 // rank inside the (warp, digit) group | digit << 16 (if kStoreDigit)
-        if (full_tile) {
-            mbar_wait(&mbar[cur], (it >> 1) & 1);
+        if (by_tma) {
+            mbar_wait(&mbar[cur], (phase >> cur) & 1u);
+            phase ^= 1u << cur;
             const Item* src = buf + wbase + lane;
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) key[i] = src[i * 32];
+        }
+        else if (full_tile) {
+            const Item* src = in + tile_base + wbase + lane;
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) key[i] = src[i * 32];
         }
@@ -277,16 +322,17 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
         // ---- per-digit tile count; publish PARTIAL as early as possible; start the look-back loads
         u32 count = 0, my_start = 0;
         u32 lbv[PF ? LB : 1];
+        u32* const my_status = status + (size_t)ti.row * RADIX + tid;       // predecessor k: my_status - k * RADIX
         if (tid < RADIX) {
 #pragma unroll
             for (int w = 0; w < NWARPS; ++w) count += whist[w * RADIX + tid];
             u32 pub = count;
             if (!full_tile && tid == RADIX - 1) pub -= (u32)TILE - tile_valid;      // padding is not data
-            st_relaxed_u32(&status[(size_t)t * RADIX + tid], pub | (t == 0 ? FLAG_INCL : FLAG_PARTIAL));
+            st_relaxed_u32(my_status, pub | (ti.idx == 0 ? FLAG_INCL : FLAG_PARTIAL));
             if (PF) {
 #pragma unroll
                 for (int k = 0; k < LB; ++k)
-                    lbv[PF ? k : 0] = ((int)t - 1 - k >= 0) ? ld_relaxed_u32(&status[(size_t)(t - 1 - k) * RADIX + tid]) : FLAG_INCL;
+                    lbv[PF ? k : 0] = ((u32)(k + 1) <= ti.idx) ? ld_relaxed_u32(my_status - (size_t)(k + 1) * RADIX) : FLAG_INCL;
             }
             u32 incl = count;
 #pragma unroll
@@ -329,12 +375,12 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
             }
         }
 
-        // ---- decoupled look-back (threads 0..RADIX-1, one digit each, LB predecessors per round trip; the first
-        // batch was requested before the scatter)
+        // ---- decoupled look-back inside the tile's segment (threads 0..RADIX-1, one digit each, LB predecessors per
+        // round trip; the first batch was requested before the scatter)
         if (tid < RADIX) {
             u32 excl = 0;
-            if (t > 0 && !(DBG && (dbg & 1))) {
-                int look = (int)t - 1;
+            if (ti.idx > 0 && !(DBG && (dbg & 1))) {
+                u32 back = 1;              // distance of the next predecessor to consume
                 bool done = false;
                 u32 v[LB];
                 if (PF) {
@@ -344,7 +390,7 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
                 else {
 #pragma unroll
                     for (int k = 0; k < LB; ++k)
-                        v[k] = (look - k >= 0) ? ld_relaxed_u32(&status[(size_t)(look - k) * RADIX + tid]) : FLAG_INCL;
+                        v[k] = (back + k <= ti.idx) ? ld_relaxed_u32(my_status - (size_t)(back + k) * RADIX) : FLAG_INCL;
                 }
                 while (true) {
                     bool stalled = false;
@@ -352,20 +398,20 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
                     for (int k = 0; k < LB; ++k) {
                         if (!done && !stalled) {
                             if (v[k] & FLAG_INCL) { excl += v[k] & VALUE_MASK; done = true; }
-                            else if (v[k] & FLAG_PARTIAL) { excl += v[k] & VALUE_MASK; look--; }
+                            else if (v[k] & FLAG_PARTIAL) { excl += v[k] & VALUE_MASK; back++; }
                             else stalled = true;
                         }
                     }
                     if (done) break;
 #pragma unroll
                     for (int k = 0; k < LB; ++k)
-                        v[k] = (look - k >= 0) ? ld_relaxed_u32(&status[(size_t)(look - k) * RADIX + tid]) : FLAG_INCL;
+                        v[k] = (back + k <= ti.idx) ? ld_relaxed_u32(my_status - (size_t)(back + k) * RADIX) : FLAG_INCL;
                 }
                 u32 pub = count;
                 if (!full_tile && tid == RADIX - 1) pub -= (u32)TILE - tile_valid;
-                st_relaxed_u32(&status[(size_t)t * RADIX + tid], (excl + pub) | FLAG_INCL);
+                st_relaxed_u32(my_status, (excl + pub) | FLAG_INCL);
             }
-            goff[tid] = gbase[tid] + excl - my_start;
+            goff[tid] = gb[tid] + excl - my_start;
         }
         __syncthreads();
 
@@ -431,12 +477,13 @@ inline int sweep_debug() {
     return f;
 }
 
-template <int WORDS, int THREADS, int WPT, int MINB, class DigitFn, bool DBG = false>
-int launch_partition_v(tg_ctx* ctx, const void* in, void* out, u32 n, const DigitFn& fn, const u32* gbase, u32* status) {
+template <int WORDS, int THREADS, int WPT, int MINB, class DigitFn, bool SEG = false, bool DBG = false>
+int launch_partition_v(tg_ctx* ctx, const void* in, void* out, u32 n, const DigitFn& fn, const u32* gbase, u32* status,
+                       const SegList& sl = SegList{ nullptr, nullptr, 0 }) {
     typedef typename ItemT<WORDS>::type Item;
     constexpr int IPT = WPT / WORDS;
     typedef SweepCfg<WORDS, THREADS, IPT> C;
-    auto kern = partition_kernel<WORDS, THREADS, IPT, MINB, DigitFn, DBG>;
+    auto kern = partition_kernel<WORDS, THREADS, IPT, MINB, DigitFn, SEG, DBG>;
     int ctas_per_sm = 0;
     auto it = ctx->kernel_cfg.find((const void*)kern);
     if (it != ctx->kernel_cfg.end()) ctas_per_sm = it->second;
@@ -448,10 +495,11 @@ int launch_partition_v(tg_ctx* ctx, const void* in, void* out, u32 n, const Digi
         if (ctas_per_sm > MINB) ctas_per_sm = MINB;
         ctx->kernel_cfg[(const void*)kern] = ctas_per_sm;
     }
-    u32 num_tiles = (n + C::TILE - 1) / C::TILE;
+    u32 num_tiles = SEG ? sl.num_tiles : (n + C::TILE - 1) / C::TILE;
+    if (num_tiles == 0) return TG_OK;
     int grid = ctx->sm_count * ctas_per_sm;
     if (grid > (int)num_tiles) grid = (int)num_tiles;
-    TG_LAUNCH_T(ctx, TG_K_PARTITION, kern, grid, THREADS, C::SMEM, (const Item*)in, (Item*)out, n, fn, gbase, status, DBG ? sweep_debug() : 0);
+    TG_LAUNCH_T(ctx, TG_K_PARTITION, kern, grid, THREADS, C::SMEM, (const Item*)in, (Item*)out, n, fn, gbase, status, sl, DBG ? sweep_debug() : 0);
     return TG_OK;
 }
 
@@ -461,12 +509,12 @@ int launch_partition(tg_ctx* ctx, const void* in, void* out, u32 n, const DigitF
 #ifdef TG_DBG_BUILD
     if (sweep_debug()) {
         switch (sweep_cfg()) {
-        case 1: return launch_partition_v<WORDS, 256, 16, 2, DigitFn, true>(ctx, in, out, n, fn, gbase, status);
-        case 2: return launch_partition_v<WORDS, 256, 16, 3, DigitFn, true>(ctx, in, out, n, fn, gbase, status);
-        case 3: return launch_partition_v<WORDS, 384, 16, 2, DigitFn, true>(ctx, in, out, n, fn, gbase, status);
-        case 4: return launch_partition_v<WORDS, 512, 8, 2, DigitFn, true>(ctx, in, out, n, fn, gbase, status);
-        case 6: return launch_partition_v<WORDS, 512, 8, 3, DigitFn, true>(ctx, in, out, n, fn, gbase, status);
-        default: return launch_partition_v<WORDS, 512, 16, 1, DigitFn, true>(ctx, in, out, n, fn, gbase, status);
+        case 1: return launch_partition_v<WORDS, 256, 16, 2, DigitFn, false, true>(ctx, in, out, n, fn, gbase, status);
+        case 2: return launch_partition_v<WORDS, 256, 16, 3, DigitFn, false, true>(ctx, in, out, n, fn, gbase, status);
+        case 3: return launch_partition_v<WORDS, 384, 16, 2, DigitFn, false, true>(ctx, in, out, n, fn, gbase, status);
+        case 4: return launch_partition_v<WORDS, 512, 8, 2, DigitFn, false, true>(ctx, in, out, n, fn, gbase, status);
+        case 6: return launch_partition_v<WORDS, 512, 8, 3, DigitFn, false, true>(ctx, in, out, n, fn, gbase, status);
+        default: return launch_partition_v<WORDS, 512, 16, 1, DigitFn, false, true>(ctx, in, out, n, fn, gbase, status);
         }
     }
 #endif
@@ -479,6 +527,28 @@ int launch_partition(tg_ctx* ctx, const void* in, void* out, u32 n, const DigitF
     case 6: return launch_partition_v<WORDS, 512, 8, 3, DigitFn>(ctx, in, out, n, fn, gbase, status);
     case 7: return launch_partition_v<WORDS, 1024, 8, 1, DigitFn>(ctx, in, out, n, fn, gbase, status);
     default: return launch_partition_v<WORDS, 512, 16, 1, DigitFn>(ctx, in, out, n, fn, gbase, status);
+    }
+}
+
+// items per tile of the selected launch configuration (the host builds segmented tile lists with it)
+template <int WORDS>
+inline u32 tile_items() {
+    const SweepVariant& v = kSweepVariants[sweep_cfg()];
+    return (u32)v.threads * (u32)(v.wpt / WORDS);
+}
+
+// one partition pass over independent segments (see SegList); status = sl.num_tiles * RADIX zeroed words
+template <int WORDS, class DigitFn>
+int launch_partition_seg(tg_ctx* ctx, const void* in, void* out, const DigitFn& fn, u32* status, const SegList& sl) {
+    switch (sweep_cfg()) {
+    case 1: return launch_partition_v<WORDS, 256, 16, 2, DigitFn, true>(ctx, in, out, 0, fn, nullptr, status, sl);
+    case 2: return launch_partition_v<WORDS, 256, 16, 3, DigitFn, true>(ctx, in, out, 0, fn, nullptr, status, sl);
+    case 3: return launch_partition_v<WORDS, 384, 16, 2, DigitFn, true>(ctx, in, out, 0, fn, nullptr, status, sl);
+    case 4: return launch_partition_v<WORDS, 512, 8, 2, DigitFn, true>(ctx, in, out, 0, fn, nullptr, status, sl);
+    case 5: return launch_partition_v<WORDS, 256, 8, 4, DigitFn, true>(ctx, in, out, 0, fn, nullptr, status, sl);
+    case 6: return launch_partition_v<WORDS, 512, 8, 3, DigitFn, true>(ctx, in, out, 0, fn, nullptr, status, sl);
+    case 7: return launch_partition_v<WORDS, 1024, 8, 1, DigitFn, true>(ctx, in, out, 0, fn, nullptr, status, sl);
+    default: return launch_partition_v<WORDS, 512, 16, 1, DigitFn, true>(ctx, in, out, 0, fn, nullptr, status, sl);
     }
 }
 

@@ -9,6 +9,9 @@
 // HBM traffic: n*s for the histogram + per executed pass n*s read + n*s write (s = item bytes).
 #include "tg_partition.cuh"
 #include "tg_keys.cuh"
+#include "tg_segmented.cuh"
+
+#include <algorithm>
 
 using namespace tgp;
 
@@ -290,12 +293,182 @@ bool prefix_sort_enabled() {
     return on != 0;
 }
 
+bool segmented_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("TG_SEGMENTED"); on = e ? atoi(e) : 1; }
+    return on != 0;
+}
+
+// `npos` stable passes (digit positions pos[0..npos), least significant first) inside the segments given by the
+// histogram of the digit the items are currently partitioned by (seg_size on the host, seg_start on the device)
+template <int WORDS>
+int run_segmented_passes(tg_ctx* ctx, const PassList& pl, const int* pos, int npos, const u32* seg_size,
+                         const u32* d_seg_start, void** src, void** dst) {
+    typedef typename ItemT<WORDS>::type Item;
+    if (npos == 0) return TG_OK;
+    if (npos > 4) return tg_set_error(ctx, TG_ERR_ARG, "segmented passes: at most 4 digit positions");
+    // NOTE: the pinned staging buffer is reused by the next build_tile_list: the copy of this list must have been
+    // consumed (stream order) before the host overwrites it -> synchronise first
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    uint4* d_tiles;
+    u32 total = 0;
+    TG_TRY(build_tile_list(ctx, RADIX, seg_size, tile_items<WORDS>(), WS_SEG_TILES, &d_tiles, &total));
+    if (total == 0) return TG_OK;
+    u32* tables;       // segcount [seg][npos][RADIX] | segbase [pos][seg][RADIX]
+    const size_t table_words = (size_t)RADIX * npos * RADIX;
+    TG_TRY(tg_ws_get(ctx, WS_SEG_TABLES, 2 * table_words * 4, (void**)&tables));
+    u32* segcount = tables;
+    u32* segbase = tables + table_words;
+    u32* status;
+    const size_t pass_status_words = (size_t)total * RADIX;
+    TG_TRY(tg_ws_get(ctx, WS_SORT_STATUS2, (size_t)npos * pass_status_words * 4, (void**)&status));
+    TG_CUDA(ctx, cudaMemsetAsync(segcount, 0, table_words * 4, ctx->stream));
+    TG_CUDA(ctx, cudaMemsetAsync(status, 0, (size_t)npos * pass_status_words * 4, ctx->stream));
+    SegList sl = { d_tiles, nullptr, total };
+    DigitList<RadixDigit> dl;
+    dl.n = npos;
+    for (int i = 0; i < 4; ++i) {
+        const int q = pos[i < npos ? i : 0];
+        dl.fn[i] = RadixDigit{ (int)pl.word[q], (int)pl.shift[q], pl.flip };
+    }
+    int grid = ctx->sm_count * 4;
+    if ((u32)grid > total) grid = (int)total;
+    TG_LAUNCH_T(ctx, TG_K_SEGCOUNT, (seg_count_kernel<WORDS, RadixDigit>), grid, 512, 0, (const Item*)*src, sl, dl, segcount);
+    TG_LAUNCH(ctx, seg_scan_kernel, dim3(RADIX, npos), RADIX, 0, segcount, d_seg_start, npos, RADIX, segbase);
+    for (int i = 0; i < npos; ++i) {
+        RadixDigit fn = { (int)pl.word[pos[i]], (int)pl.shift[pos[i]], pl.flip };
+        sl.segbase = segbase + (size_t)i * RADIX * RADIX;
+        TG_TRY((launch_partition_seg<WORDS, RadixDigit>(ctx, *src, *dst, fn, status + (size_t)i * pass_status_words, sl)));
+        void* t = *src; *src = *dst; *dst = t;
+    }
+    return TG_OK;
+}
+
+// finishing pass of the prefix sort over src -> dst; *ok = no group was too long
+template <int WORDS>
+int run_fixup(tg_ctx* ctx, const tg_key_desc* desc, bool plain_u64, int pass0, const void* src, void* dst, size_t n, u32* d_fail,
+              bool* ok) {
+    typedef typename ItemT<WORDS>::type Item;
+    KeyView kv;
+    if (make_key_view(desc, &kv) != TG_OK) return tg_set_error(ctx, TG_ERR_ARG, "radix sort: unsupported key descriptor");
+    PrefixMask pm = prefix_mask(desc, pass0);
+    const u32 grid = (u32)((n + FIX_TILE - 1) / FIX_TILE);
+    TG_CUDA(ctx, cudaMemsetAsync(d_fail, 0, 4, ctx->stream));
+    if (plain_u64 && !desc->descending)
+        TG_LAUNCH_T(ctx, TG_K_FIXUP, (prefix_fixup_kernel<WORDS, true>), grid, FIX_THREADS, 0, (const Item*)src, (Item*)dst, (u32)n, kv, pm, d_fail);
+    else
+        TG_LAUNCH_T(ctx, TG_K_FIXUP, (prefix_fixup_kernel<WORDS, false>), grid, FIX_THREADS, 0, (const Item*)src, (Item*)dst, (u32)n, kv, pm, d_fail);
+    u32* h_fail = (u32*)ctx->pinned;
+    TG_CUDA(ctx, cudaMemcpyAsync(h_fail, d_fail, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *ok = *h_fail == 0;
+    return TG_OK;
+}
+
+// Speculative fast path of the prefix sort: assumes the most significant key byte is an active digit with many
+// values.  One read (chunk histograms of that digit + OR/AND of the keys), the pass on it as a segmented pass over the
+// chunks, the other K-1 prefix digits inside its buckets, the finishing pass.  *taken = the items in *src are sorted;
+// otherwise *src holds a permutation of the input and the caller runs the general path.
+template <int WORDS>
+int prefix_sort_fast(tg_ctx* ctx, const tg_key_desc* desc, const PassList& pl, bool plain_u64, size_t n, void** src, void** dst,
+                     bool* taken) {
+    typedef typename ItemT<WORDS>::type Item;
+    *taken = false;
+    const int K = prefix_digits_for(n);
+    if (!prefix_sort_enabled() || !segmented_enabled() || pl.npass < K + 2 || n < (1u << 15)) return TG_OK;
+    if (ctx->prefix_sort_penalty > 0) return TG_OK;          // counted down by the general path
+    if (ctx->prefix_spec_penalty > 0) { ctx->prefix_spec_penalty--; return TG_OK; }
+    const int top = pl.npass - 1;
+    const u32 tile = tile_items<WORDS>();
+    const ChunkGeom cg = chunk_geometry<WORDS>(ctx, n);
+    const u32 chunk_items = cg.chunk_items;
+    const int nchunks = cg.nchunks;
+
+    u32* tab;      // chunkcount [nchunks][RADIX] | chunk segbase [nchunks][RADIX] | totals [RADIX] | gbase [RADIX] | orand u64[4] | fail
+    const size_t cw = (size_t)nchunks * RADIX;
+    TG_TRY(tg_ws_get(ctx, WS_SORT_HIST2, (2 * cw + 2 * RADIX + 16) * 4, (void**)&tab));
+    u32* chunkcount = tab;
+    u32* chunkbase = tab + cw;
+    u32* totals = chunkbase + cw;
+    u32* gbase_top = totals + RADIX;
+    u64* orand = (u64*)(gbase_top + RADIX);
+    u32* fail = (u32*)(orand + 4);
+    u64* h_orand = (u64*)ctx->pinned;
+    u32* h_totals = (u32*)(h_orand + 4);
+    u64* h_init = h_orand + 512;                 // separate pinned words: read by the H2D copy below
+    for (int w = 0; w < 2; ++w) { h_init[2 * w] = 0; h_init[2 * w + 1] = ~0ull; }
+    TG_CUDA(ctx, cudaMemcpyAsync(orand, h_init, 32, cudaMemcpyHostToDevice, ctx->stream));
+    const RadixDigit top_fn = { (int)pl.word[top], (int)pl.shift[top], pl.flip };
+    TG_LAUNCH_T(ctx, TG_K_RADIX_HIST, (chunk_hist_kernel<WORDS, RadixDigit, true>), nchunks, 512, 0, (const Item*)*src, (u32)n, chunk_items,
+                top_fn, chunkcount, orand);
+    TG_LAUNCH(ctx, chunk_scan_kernel, 1, 4 * RADIX, 0, chunkcount, nchunks, totals, gbase_top, chunkbase);
+    TG_CUDA(ctx, cudaMemcpyAsync(h_orand, orand, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    TG_CUDA(ctx, cudaMemcpyAsync(h_totals, totals, RADIX * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    // the chunk tile list does not depend on the data: build and upload it while the histogram runs
+    std::vector<u32> chunk_size(nchunks, chunk_items);
+    chunk_size[nchunks - 1] = (u32)(n - (size_t)(nchunks - 1) * chunk_items);
+    uint4* d_ctiles;
+    u32 ctotal = 0;
+    TG_TRY(build_tile_list(ctx, nchunks, chunk_size.data(), tile, WS_SEG_TILES2, &d_ctiles, &ctotal));
+    u32* cstatus;
+    TG_TRY(tg_ws_get(ctx, WS_SORT_STATUS, (size_t)ctotal * RADIX * 4, (void**)&cstatus));
+    TG_CUDA(ctx, cudaMemsetAsync(cstatus, 0, (size_t)ctotal * RADIX * 4, ctx->stream));
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+
+    // which digit positions are active (not constant over all keys), least significant first
+    int active[MAX_PASSES], nactive = 0;
+    for (int p = 0; p < pl.npass; ++p) {
+        const u64 diff = h_orand[2 * pl.word[p]] ^ h_orand[2 * pl.word[p] + 1];
+        if ((diff >> pl.shift[p]) & 0xffu) active[nactive++] = p;
+    }
+    int nonempty = 0;
+    for (int d = 0; d < RADIX; ++d) nonempty += h_totals[d] ? 1 : 0;
+    if (nactive < K + 2 || active[nactive - 1] != top || nonempty < 32) {
+        ctx->prefix_spec_penalty = 8;         // the guess was wrong for this kind of input: do not pay for it every time
+        return TG_OK;
+    }
+    // (1) most significant digit: segmented pass over the chunks
+    {
+        SegList sl = { d_ctiles, chunkbase, ctotal };
+        RadixDigit fn = { (int)pl.word[top], (int)pl.shift[top], pl.flip };
+        TG_TRY((launch_partition_seg<WORDS, RadixDigit>(ctx, *src, *dst, fn, cstatus, sl)));
+        void* t = *src; *src = *dst; *dst = t;
+    }
+    // (2) the other K-1 prefix digits inside the buckets of (1)
+    TG_TRY((run_segmented_passes<WORDS>(ctx, pl, active + (nactive - K), K - 1, h_totals, gbase_top, src, dst)));
+    // (3) finishing pass
+    bool ok = false;
+    TG_TRY((run_fixup<WORDS>(ctx, desc, plain_u64, active[nactive - K], *src, *dst, n, fail, &ok)));
+    if (ok) {
+        void* t = *src; *src = *dst; *dst = t;
+        *taken = true;
+    }
+    else {
+        ctx->prefix_sort_penalty = 8;
+        ctx->prefix_sort_fallbacks++;
+    }
+    return TG_OK;
+}
+
 // The sorted items end up in *result (= d_items or d_tmp); result == nullptr asks for them in d_items.
 template <int WORDS>
 int radix_sort_impl(tg_ctx* ctx, const tg_key_desc* desc, const PassList& pl, void* d_items, void* d_tmp, size_t n,
                     void** result) {
     typedef typename ItemT<WORDS>::type Item;
     const u32 num_tiles = num_tiles_for<WORDS>(n);
+    void* src = d_items;
+    void* dst = d_tmp;
+    bool plain_u64 = WORDS == 1 && pl.npass == 8;
+    for (int p = 0; p < pl.npass && plain_u64; ++p) plain_u64 = pl.word[p] == 0 && pl.shift[p] == 8 * p;
+
+    bool fast = false;
+    TG_TRY((prefix_sort_fast<WORDS>(ctx, desc, pl, plain_u64, n, &src, &dst, &fast)));
+    if (fast) {
+        if (result) *result = src;
+        else if (src != d_items)
+            TG_LAUNCH(ctx, copy_items_kernel<WORDS>, ctx->sm_count * 8, 256, 0, (const Item*)src, (Item*)d_items, n);
+        return TG_OK;
+    }
 
     u32* hist;      // [npass][RADIX] counts | [npass][RADIX] bases | [npass] skip | fail flag
     size_t hist_words = (size_t)2 * pl.npass * RADIX + MAX_PASSES + 4;
@@ -310,23 +483,22 @@ int radix_sort_impl(tg_ctx* ctx, const tg_key_desc* desc, const PassList& pl, vo
     TG_CUDA(ctx, cudaMemsetAsync(hist, 0, hist_words * 4, ctx->stream));
     TG_CUDA(ctx, cudaMemsetAsync(status, 0, status_bytes, ctx->stream));
 
-    bool plain_u64 = WORDS == 1 && pl.npass == 8;
-    for (int p = 0; p < pl.npass && plain_u64; ++p) plain_u64 = pl.word[p] == 0 && pl.shift[p] == 8 * p;
     if (plain_u64)
-        TG_LAUNCH_T(ctx, TG_K_RADIX_HIST, radix_hist_u64_kernel, ctx->sm_count * 2, 512, 0, (const u64*)d_items, n, pl.flip, hist);
+        TG_LAUNCH_T(ctx, TG_K_RADIX_HIST, radix_hist_u64_kernel, ctx->sm_count * 2, 512, 0, (const u64*)src, n, pl.flip, hist);
     else
-        TG_LAUNCH_T(ctx, TG_K_RADIX_HIST, radix_hist_kernel<WORDS>, ctx->sm_count * 2, 512, pl.npass * RADIX * 4, (const Item*)d_items, n, pl, hist);
+        TG_LAUNCH_T(ctx, TG_K_RADIX_HIST, radix_hist_kernel<WORDS>, ctx->sm_count * 2, 512, pl.npass * RADIX * 4, (const Item*)src, n, pl, hist);
     TG_LAUNCH(ctx, scan_hist_kernel, 1, RADIX, 0, hist, gbase, skip, pl.npass, (u32)n);
+    // skip flags and the digit histograms themselves (segment sizes of the segmented passes) to the host
     u32* h_skip = (u32*)ctx->pinned;
+    u32* h_hist = h_skip + MAX_PASSES;
     TG_CUDA(ctx, cudaMemcpyAsync(h_skip, skip, pl.npass * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TG_CUDA(ctx, cudaMemcpyAsync(h_hist, hist, (size_t)pl.npass * RADIX * 4, cudaMemcpyDeviceToHost, ctx->stream));
     TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 
     int active[MAX_PASSES], nactive = 0;      // digit positions where the keys differ, least significant first
     for (int p = 0; p < pl.npass; ++p)
         if (!h_skip[p]) active[nactive++] = p;
 
-    void* src = d_items;
-    void* dst = d_tmp;
     auto run_pass = [&](int p) -> int {
         RadixDigit fn = { (int)pl.word[p], (int)pl.shift[p], pl.flip };
         TG_TRY((launch_partition<WORDS, RadixDigit>(ctx, src, dst, (u32)n, fn, gbase + (size_t)p * RADIX,
@@ -339,19 +511,20 @@ int radix_sort_impl(tg_ctx* ctx, const tg_key_desc* desc, const PassList& pl, vo
     const int K = prefix_digits_for(n);
     bool done = false;
     if (prefix_sort_enabled() && nactive >= K + 2 && ctx->prefix_sort_penalty == 0) {
-        for (int a = nactive - K; a < nactive; ++a) TG_TRY(run_pass(active[a]));
-        KeyView kv;
-        if (make_key_view(desc, &kv) != TG_OK) return tg_set_error(ctx, TG_ERR_ARG, "radix sort: unsupported key descriptor");
-        PrefixMask pm = prefix_mask(desc, active[nactive - K]);
-        const u32 grid = (u32)((n + FIX_TILE - 1) / FIX_TILE);
-        if (plain_u64 && !desc->descending)
-            TG_LAUNCH_T(ctx, TG_K_FIXUP, (prefix_fixup_kernel<WORDS, true>), grid, FIX_THREADS, 0, (const Item*)src, (Item*)dst, (u32)n, kv, pm, fail);
+        const int top = active[nactive - 1];
+        int nonempty = 0;
+        for (int d = 0; d < RADIX; ++d) nonempty += h_hist[top * RADIX + d] ? 1 : 0;
+        if (segmented_enabled() && K >= 2 && nonempty >= 32) {
+            // most significant digit first (global pass), then the other K-1 digits inside its buckets
+            TG_TRY(run_pass(top));
+            TG_TRY((run_segmented_passes<WORDS>(ctx, pl, active + (nactive - K), K - 1, h_hist + top * RADIX,
+                                                 gbase + (size_t)top * RADIX, &src, &dst)));
+        }
         else
-            TG_LAUNCH_T(ctx, TG_K_FIXUP, (prefix_fixup_kernel<WORDS, false>), grid, FIX_THREADS, 0, (const Item*)src, (Item*)dst, (u32)n, kv, pm, fail);
-        u32* h_fail = (u32*)ctx->pinned;
-        TG_CUDA(ctx, cudaMemcpyAsync(h_fail, fail, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (*h_fail == 0) {
+            for (int a = nactive - K; a < nactive; ++a) TG_TRY(run_pass(active[a]));
+        bool ok = false;
+        TG_TRY((run_fixup<WORDS>(ctx, desc, plain_u64, active[nactive - K], src, dst, n, fail, &ok)));
+        if (ok) {
             void* t = src; src = dst; dst = t;
             done = true;
         }

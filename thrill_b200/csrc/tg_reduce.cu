@@ -14,6 +14,7 @@
 //   post phase  : open-addressing table in HBM (16-byte slots, atomicCAS on the key, native atomics on the
 //                 value), sized from the number of partial aggregates, then compaction of the used slots
 #include "tg_partition.cuh"
+#include "tg_segmented.cuh"
 
 using namespace tgp;
 
@@ -333,6 +334,220 @@ int run_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 m, void* d_out, u64
     return read_cursor(ctx, sc, out_distinct);
 }
 
+// ---- partitioned aggregation -------------------------------------------------------------------------------------
+// An open-addressing table in HBM makes one random 32-byte sector access (plus an L2 atomic) per record: 1.7 TB/s of
+// sector traffic for 0.3 TB/s of useful data (profiles/r1d).  Shared memory is the only place where the probing and the
+// reduce function are cheap, so the records are first brought into an order in which every CTA sees few distinct keys:
+//   two stable partition passes by two 8-bit digits of Hash128to64(0,key) (chunked + segmented, tg_segmented.cuh)
+//   -> 65536 segments with disjoint key sets, ~n/65536 records each
+//   -> "units" of whole consecutive segments (<= AGG_UNIT records) are reduced in a shared-memory probing table
+//      (ReduceProbingHashTable::Insert, core/reduce_probing_hash_table.hpp:190-268, one table per unit) and emitted;
+//      a segment longer than a unit (a hot key) is cut into pieces whose partial aggregates are merged afterwards by the
+//      HBM table (few items).
+// The hash bits used here (24..51) are not the ones that pick the destination worker (hash % p).
+constexpr int AGG_THREADS = 256;
+constexpr int AGG_RPT = 8;                         // records per thread
+constexpr int AGG_UNIT = AGG_THREADS * AGG_RPT;    // 2048 records
+constexpr u32 AGG_SLOTS = 2 * AGG_UNIT;            // load factor <= 1/2
+constexpr int AGG_SHIFT1 = 24, AGG_SHIFT2 = 32, AGG_SHIFT_SLOT = 40;
+constexpr size_t AGG_MIN_ITEMS = 1u << 18;         // below: the HBM table alone
+
+struct HashLevelDigit {
+    int shift;
+    static constexpr bool kStoreDigit = true;
+    __device__ __forceinline__ u32 operator()(const ulonglong2& v, u32) const { return (u32)(key_hash(v.x) >> shift) & (RADIX - 1); }
+};
+
+// register-level reduce function (the warp-uniform fast path)
+__device__ __forceinline__ u64 op_combine(int op, u64 a, u64 b) {
+    switch (op) {
+    case TG_OP_SUM_F64: return (u64)__double_as_longlong(__longlong_as_double((long long)a) + __longlong_as_double((long long)b));
+    case TG_OP_SUM_U64: return a + b;
+    case TG_OP_MIN_U64: return a < b ? a : b;
+    case TG_OP_MAX_U64: return a > b ? a : b;
+    case TG_OP_MIN_F64: return __longlong_as_double((long long)b) < __longlong_as_double((long long)a) ? b : a;
+    case TG_OP_MAX_F64: return __longlong_as_double((long long)a) < __longlong_as_double((long long)b) ? b : a;
+    default: return a;          // TG_OP_FIRST
+    }
+}
+
+__global__ void __launch_bounds__(AGG_THREADS, 3)
+agg_units_kernel(const ulonglong2* __restrict__ in, const uint2* __restrict__ units /* {first record, records | partial << 31} */,
+                 u32 nunits, int op, u64 ident, ulonglong2* __restrict__ out, u64* __restrict__ cursor,
+                 ulonglong2* __restrict__ dup_out, u64* __restrict__ dup_cursor, u64* __restrict__ zero_slot) {
+    extern __shared__ __align__(16) unsigned char agg_smem[];
+    u64* const keys = reinterpret_cast<u64*>(agg_smem);
+    u64* const vals = keys + AGG_SLOTS;
+    u32* const scratch = reinterpret_cast<u32*>(vals + AGG_SLOTS);      // 36 words, 8-byte aligned
+    const u32 lane = lane_id();
+    for (u32 unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+        const uint2 u = __ldg(&units[unit]);
+        const u32 start = u.x, len = u.y & 0x7fffffffu;
+        const bool partial = (u.y >> 31) != 0;
+        for (u32 i = threadIdx.x; i < AGG_SLOTS; i += AGG_THREADS) { keys[i] = 0; vals[i] = ident; }
+        __syncthreads();
+        u64 key[AGG_RPT], val[AGG_RPT];
+        bool valid[AGG_RPT];
+#pragma unroll
+        for (int r = 0; r < AGG_RPT; ++r) {
+            const u32 i = r * AGG_THREADS + threadIdx.x;
+            valid[r] = i < len;
+            ulonglong2 kv = valid[r] ? in[(size_t)start + i] : make_ulonglong2(0, 0);
+            key[r] = kv.x; val[r] = kv.y;
+        }
+#pragma unroll
+        for (int r = 0; r < AGG_RPT; ++r) {
+            // a warp whose 32 records carry the same key (a hot key's segment) reduces them in registers first
+            const u64 k0 = __shfl_sync(0xffffffffu, key[r], 0);
+            const bool uniform = __all_sync(0xffffffffu, valid[r] && key[r] == k0);
+            u64 v = val[r];
+            bool mine = valid[r];
+            if (uniform) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    // lower lane = earlier record: keeps TG_OP_FIRST's "first"
+                    u64 other = __shfl_down_sync(0xffffffffu, v, o);
+                    v = op_combine(op, v, other);
+                }
+                mine = lane == 0;
+            }
+            if (!mine) continue;
+            if (key[r] == 0) {
+                // Key() == 0: reduced in a side slot, never probed (reduce_probing_hash_table.hpp:195-218)
+                u64 prev = atomicCAS(&zero_slot[0], 0ull, 1ull);
+                op_apply(op, &zero_slot[1], v, prev == 0);
+                continue;
+            }
+            u32 slot = (u32)(key_hash(key[r]) >> AGG_SHIFT_SLOT) & (AGG_SLOTS - 1);
+            bool claimed = false;
+            while (true) {
+                u64 k = *(volatile u64*)&keys[slot];
+                if (k == 0) {
+                    k = atomicCAS(&keys[slot], 0ull, key[r]);
+                    claimed = k == 0;
+                    if (claimed) break;
+                }
+                if (k == key[r]) break;
+                slot = (slot + 1) & (AGG_SLOTS - 1);
+            }
+            op_apply(op, &vals[slot], v, claimed);
+        }
+        __syncthreads();
+        // emit the table (FlushPartitionEmit, reduce_probing_hash_table.hpp:443-482)
+        constexpr int EI = AGG_SLOTS / AGG_THREADS;
+        u64 ek[EI], ev[EI];
+        bool has[EI];
+#pragma unroll
+        for (int j = 0; j < EI; ++j) {
+            const u32 i = j * AGG_THREADS + threadIdx.x;
+            ek[j] = keys[i]; ev[j] = vals[i];
+            has[j] = ek[j] != 0;
+        }
+        if (partial) emit_block<EI>(dup_out, dup_cursor, ek, ev, has, scratch);
+        else emit_block<EI>(out, cursor, ek, ev, has, scratch);
+        __syncthreads();
+    }
+}
+
+int run_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 m, void* d_out, u64* out_distinct);
+
+// n records -> distinct keys in d_out (capacity n + 1)
+int run_partitioned_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 n, void* d_out, u64* out_distinct) {
+    if (n < AGG_MIN_ITEMS || n >= (1u << 30) || getenv("TG_REDUCE_HBM_TABLE")) return run_aggregate(ctx, op, d_in, n, d_out, out_distinct);
+    const u64 ident = (op == TG_OP_MIN_U64) ? ~0ull : (op == TG_OP_MIN_F64) ? 0x7FF0000000000000ull
+                    : (op == TG_OP_MAX_F64) ? 0xFFF0000000000000ull : 0ull;
+    void *bufA, *bufB;
+    TG_TRY(tg_ws_get(ctx, WS_AUX, (n + 2) * 16, &bufA));
+    TG_TRY(tg_ws_get(ctx, WS_AUX2, (n + 2) * 16, &bufB));
+    // (1) first hash digit: chunked pass
+    u32 *d_tot1, *d_gbase1;
+    HashLevelDigit fn1 = { AGG_SHIFT1 };
+    TG_TRY((partition_chunked<2, HashLevelDigit>(ctx, d_in, bufA, n, fn1, &d_tot1, &d_gbase1)));
+    u32* h_tot1 = (u32*)ctx->pinned;
+    TG_CUDA(ctx, cudaMemcpyAsync(h_tot1, d_tot1, RADIX * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // (2) second hash digit inside the buckets of the first: segmented pass
+    uint4* d_tiles;
+    u32 total = 0;
+    TG_TRY(build_tile_list(ctx, RADIX, h_tot1, tile_items<2>(), WS_SEG_TILES, &d_tiles, &total));
+    u32* tables;       // segcount [seg][RADIX] | segbase [seg][RADIX]
+    const size_t table_words = (size_t)RADIX * RADIX;
+    TG_TRY(tg_ws_get(ctx, WS_SEG_TABLES, 2 * table_words * 4, (void**)&tables));
+    u32* segcount = tables;
+    u32* segbase = tables + table_words;
+    u32* status;
+    TG_TRY(tg_ws_get(ctx, WS_SORT_STATUS2, (size_t)total * RADIX * 4, (void**)&status));
+    TG_CUDA(ctx, cudaMemsetAsync(segcount, 0, table_words * 4, ctx->stream));
+    TG_CUDA(ctx, cudaMemsetAsync(status, 0, (size_t)total * RADIX * 4, ctx->stream));
+    SegList sl = { d_tiles, segbase, total };
+    DigitList<HashLevelDigit> dl;
+    dl.n = 1;
+    for (int i = 0; i < 4; ++i) dl.fn[i] = HashLevelDigit{ AGG_SHIFT2 };
+    int grid = ctx->sm_count * 4;
+    if ((u32)grid > total) grid = (int)total;
+    TG_LAUNCH_T(ctx, TG_K_SEGCOUNT, (seg_count_kernel<2, HashLevelDigit>), grid, 512, 0, (const ulonglong2*)bufA, sl, dl, segcount);
+    TG_LAUNCH(ctx, seg_scan_kernel, dim3(RADIX, 1), RADIX, 0, segcount, d_gbase1, 1, RADIX, segbase);
+    TG_TRY((launch_partition_seg<2, HashLevelDigit>(ctx, bufA, bufB, dl.fn[0], status, sl)));
+    // (3) units: whole consecutive segments up to AGG_UNIT records; longer segments in pieces (partial)
+    u32* h_seg;
+    TG_TRY(tg_pinned_list(ctx, table_words * 4 + (size_t)(n / AGG_UNIT + 2 * table_words + 16) * sizeof(uint2), (void**)&h_seg));
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));          // (the tile list staged in the same pinned buffer is consumed)
+    TG_CUDA(ctx, cudaMemcpyAsync(h_seg, segcount, table_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    uint2* h_units = (uint2*)(h_seg + table_words);
+    u32 nunits = 0, pos = 0, ustart = 0, ulen = 0;
+    for (size_t sgi = 0; sgi < table_words; ++sgi) {
+        const u32 c = h_seg[sgi];
+        if (c == 0) continue;
+        if (c > (u32)AGG_UNIT) {
+            if (ulen) { h_units[nunits++] = make_uint2(ustart, ulen); ulen = 0; }
+            for (u32 off = 0; off < c; off += AGG_UNIT) {
+                u32 l = c - off < (u32)AGG_UNIT ? c - off : (u32)AGG_UNIT;
+                h_units[nunits++] = make_uint2(pos + off, l | 0x80000000u);
+            }
+        }
+        else {
+            if (ulen + c > (u32)AGG_UNIT) { h_units[nunits++] = make_uint2(ustart, ulen); ulen = 0; }
+            if (ulen == 0) ustart = pos;
+            ulen += c;
+        }
+        pos += c;
+    }
+    if (ulen) h_units[nunits++] = make_uint2(ustart, ulen);
+    if (pos != (u32)n) return tg_set_error(ctx, TG_ERR_CUDA, "reduce: segment sizes add up to %u of %llu records", pos, (unsigned long long)n);
+    uint2* d_units;
+    TG_TRY(tg_ws_get(ctx, WS_SEG_TILES2, (size_t)nunits * sizeof(uint2) + 16, (void**)&d_units));
+    TG_CUDA(ctx, cudaMemcpyAsync(d_units, h_units, (size_t)nunits * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+    ReduceScratch sc;
+    TG_TRY(get_scratch(ctx, op, &sc));
+    u64* dup_cursor = sc.cursor + 1;
+    ulonglong2* d_dup = (ulonglong2*)bufA;                     // the first pass's output is dead: reuse it for the partial aggregates
+    int agrid = ctx->sm_count * 3;
+    if ((u32)agrid > nunits) agrid = (int)nunits;
+    constexpr int AGG_SMEM = AGG_SLOTS * 16 + 36 * 4 + 16;
+    if (ctx->kernel_cfg.find((const void*)agg_units_kernel) == ctx->kernel_cfg.end()) {
+        TG_CUDA(ctx, cudaFuncSetAttribute(agg_units_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AGG_SMEM));
+        ctx->kernel_cfg[(const void*)agg_units_kernel] = 3;
+    }
+    TG_LAUNCH_T(ctx, TG_K_AGGREGATE, agg_units_kernel, agrid, AGG_THREADS, AGG_SMEM, (const ulonglong2*)bufB, (const uint2*)d_units, nunits, op, ident,
+                (ulonglong2*)d_out, sc.cursor, d_dup, dup_cursor, sc.zero_slot);
+    u64* h = (u64*)ctx->pinned + 2048;
+    TG_CUDA(ctx, cudaMemcpyAsync(h, sc.cursor, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const u64 ndup = h[1];
+    // (4) merge the pieces of the long segments (and emit the zero key) through the HBM table, appended to d_out
+    u64 cap = ndup ? ndup + ndup / 2 + 64 : 0;
+    ulonglong2* tab = nullptr;
+    if (ndup) {
+        TG_TRY(tg_ws_get(ctx, WS_TABLE, cap * 16, (void**)&tab));
+        TG_LAUNCH(ctx, table_init_kernel, ctx->sm_count * 4, 512, 0, tab, cap, ident);
+        TG_LAUNCH_T(ctx, TG_K_AGGREGATE, aggregate_kernel, ctx->sm_count * 4, 512, 0, (const ulonglong2*)d_dup, ndup, op, tab, cap, sc.zero_slot);
+    }
+    TG_LAUNCH_T(ctx, TG_K_COMPACT, compact_kernel, ndup ? ctx->sm_count * 4 : 1, ndup ? 512 : 32, 0, (const ulonglong2*)tab, cap,
+                (ulonglong2*)d_out, sc.cursor, sc.zero_slot);
+    return read_cursor(ctx, sc, out_distinct);
+}
+
 int check_kv(tg_ctx* ctx, const tg_kv_desc* d) {
     if (!ctx || !d || d->item_bytes != 16 || d->op > TG_OP_FIRST)
         return tg_set_error(ctx, TG_ERR_ARG, "reduce: only 16-byte (u64 key, 8-byte value) items and TG_OP_* are supported");
@@ -346,13 +561,8 @@ extern "C" {
 int tg_hash_aggregate(tg_ctx* ctx, const tg_kv_desc* desc, const void* d_in, size_t n, void* d_out, uint64_t* out_distinct) {
     TG_TRY(check_kv(ctx, desc));
     TG_CUDA(ctx, cudaSetDevice(ctx->device));
-    // pre phase into scratch, post phase into d_out
-    void* d_pre;
-    TG_TRY(tg_ws_get(ctx, WS_AUX, preagg_out_capacity(ctx, n) * 16, &d_pre));
-    u64 m = 0;
-    TG_TRY(run_preagg(ctx, (int)desc->op, d_in, n, d_pre, &m));
     u64 distinct = 0;
-    TG_TRY(run_aggregate(ctx, (int)desc->op, d_pre, m, d_out, &distinct));
+    TG_TRY(run_partitioned_aggregate(ctx, (int)desc->op, d_in, n, d_out, &distinct));
     *out_distinct = distinct;
     return TG_OK;
 }
@@ -378,11 +588,17 @@ int tg_reduce_by_key(tg_ctx* ctx, const tg_kv_desc* desc, const void* d_in, size
     TG_CUDA(ctx, cudaSetDevice(ctx->device));
     const int op = (int)desc->op;
     const int p = ctx->nranks, me = ctx->rank;
-    // pre phase (ReducePrePhase, StartPreOp..StopPreOp: api/reduce_by_key.hpp:142-168)
+    // pre phase (ReducePrePhase, StartPreOp..StopPreOp: api/reduce_by_key.hpp:142-168): the local aggregation; with one
+    // worker it is already the result
     void* d_pre;
-    TG_TRY(tg_ws_get(ctx, WS_AUX, preagg_out_capacity(ctx, n_local) * 16, &d_pre));
+    TG_TRY(tg_ws_get(ctx, WS_OUT, (n_local + 2) * 16, &d_pre));
     u64 m = 0;
-    TG_TRY(run_preagg(ctx, op, d_in, n_local, d_pre, &m));
+    TG_TRY(run_partitioned_aggregate(ctx, op, d_in, n_local, d_pre, &m));
+    if (p == 1) {
+        *out_dptr = d_pre;
+        *out_n = (size_t)m;
+        return TG_OK;
+    }
     const void* d_post_in = d_pre;
     u64 m_post = m;
     if (p > 1) {
@@ -421,9 +637,9 @@ int tg_reduce_by_key(tg_ctx* ctx, const tg_kv_desc* desc, const void* d_in, size
     }
     // post phase (ReduceByHashPostPhase, ProcessChannel + PushData: api/reduce_by_key.hpp:176-211)
     void* d_out;
-    TG_TRY(tg_ws_get(ctx, WS_OUT, (m_post + 2) * 16, &d_out));
+    TG_TRY(tg_ws_get(ctx, WS_OUT, (m_post + 2) * 16, &d_out));      // (the pre phase's output was consumed by the partition)
     u64 distinct = 0;
-    TG_TRY(run_aggregate(ctx, op, d_post_in, m_post, d_out, &distinct));
+    TG_TRY(run_partitioned_aggregate(ctx, op, d_post_in, m_post, d_out, &distinct));
     *out_dptr = d_out;
     *out_n = (size_t)distinct;
     return TG_OK;

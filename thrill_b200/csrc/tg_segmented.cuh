@@ -1,0 +1,254 @@
+// tg_segmented.cuh — partition passes without a chained scan between tiles that run at the same time.
+//
+// A partition pass needs, for every tile and digit, the number of items with that digit in the tiles before it.
+// The chained scan ("decoupled look-back", tg_partition.cuh) gets it from the tiles themselves, which makes every tile
+// wait for the tiles processed at the same time on the other SMs (27 % of the pass, profiles/r1d).  Both forms below
+// know the bases of coarse SEGMENTS up front and list the tiles so that consecutive tiles of the processing order
+// belong to different segments; the scan chain of a tile only spans its own segment and its predecessor finished a
+// whole wave of CTAs earlier:
+//   * chunked pass   — any input: cut it into contiguous chunks, one counting read gives segbase[chunk][digit]
+//   * segmented pass — input already partitioned by a more significant digit: the buckets are the segments, items never
+//     leave their bucket, and one counting read serves every further pass inside the buckets.
+// Used by the radix sort (tg_radix_sort.cu) and by the hash aggregation (tg_reduce.cu).
+#pragma once
+#include <algorithm>
+#include <vector>
+
+#include "tg_partition.cuh"
+
+namespace tgp {
+
+// up to 4 digit functions counted in one read
+template <class DigitFn>
+struct DigitList {
+    int n;
+    DigitFn fn[4];
+};
+
+// Per-chunk histogram of fn (chunk = blockIdx.x, items [chunk*chunk_items, ...)); ORAND: also OR / AND of the item words
+// (orand[2w] = OR, orand[2w+1] = AND of word w; tells which digit positions are constant over the whole input).
+template <int WORDS, class DigitFn, bool ORAND>
+__global__ void __launch_bounds__(512) chunk_hist_kernel(const typename ItemT<WORDS>::type* __restrict__ in, u32 n, u32 chunk_items,
+                                                         const DigitFn fn, u32* __restrict__ chunkcount /* [grid][RADIX] */,
+                                                         u64* __restrict__ orand) {
+    typedef typename ItemT<WORDS>::type Item;
+    constexpr int U = 4;
+    __shared__ u32 sh[RADIX];
+    for (int i = threadIdx.x; i < RADIX; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const u32 lo = blockIdx.x * chunk_items;
+    const u32 hi = (n - lo < chunk_items) ? n : lo + chunk_items;
+    const u32 lane = lane_id();
+    u64 vor[WORDS], vand[WORDS];
+#pragma unroll
+    for (int w = 0; w < WORDS; ++w) { vor[w] = 0; vand[w] = ~0ull; }
+    for (u32 base = lo; base < hi; base += blockDim.x * U) {
+        Item v[U];
+        bool valid[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            u32 i = base + u * blockDim.x + threadIdx.x;
+            valid[u] = i < hi;
+            if (valid[u]) v[u] = in[i];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (ORAND && valid[u]) {
+#pragma unroll
+                for (int w = 0; w < WORDS; ++w) { vor[w] |= item_word(v[u], w); vand[w] &= item_word(v[u], w); }
+            }
+            const u32 d = valid[u] ? fn(v[u], base + u * blockDim.x + threadIdx.x) : 0u;
+            if (__all_sync(0xffffffffu, valid[u])) {
+                // one shared-memory atomic per warp where the whole warp agrees on the digit (constant high bytes)
+                const u32 d0 = __shfl_sync(0xffffffffu, d, 0);
+                if (__all_sync(0xffffffffu, d == d0)) { if (lane == 0) atomicAdd(&sh[d], 32u); }
+                else atomicAdd(&sh[d], 1u);
+            }
+            else if (valid[u]) atomicAdd(&sh[d], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < RADIX; i += blockDim.x) chunkcount[(size_t)blockIdx.x * RADIX + i] = sh[i];
+    if (ORAND) {
+#pragma unroll
+        for (int w = 0; w < WORDS; ++w) {
+            u32 olo = __reduce_or_sync(0xffffffffu, (u32)vor[w]), ohi = __reduce_or_sync(0xffffffffu, (u32)(vor[w] >> 32));
+            u32 alo = __reduce_and_sync(0xffffffffu, (u32)vand[w]), ahi = __reduce_and_sync(0xffffffffu, (u32)(vand[w] >> 32));
+            if (lane == 0) {
+                atomicOr(&orand[2 * w], ((u64)ohi << 32) | olo);
+                atomicAnd(&orand[2 * w + 1], ((u64)ahi << 32) | alo);
+            }
+        }
+    }
+}
+
+// totals[d], gbase[d] (exclusive scan of the totals) and segbase[chunk][d]; one CTA of 4 * RADIX threads
+static __global__ void __launch_bounds__(4 * RADIX) chunk_scan_kernel(const u32* __restrict__ chunkcount, int nchunks,
+                                                                      u32* __restrict__ totals, u32* __restrict__ gbase,
+                                                                      u32* __restrict__ segbase) {
+    __shared__ u32 part[4][RADIX];
+    __shared__ u32 warp_tot[RADIX / 32];
+    const int d = threadIdx.x & (RADIX - 1), g = threadIdx.x >> 8;
+    const int per = (nchunks + 3) / 4;
+    const int c0 = g * per, c1 = (c0 + per < nchunks) ? c0 + per : nchunks;
+    u32 sum = 0;
+#pragma unroll 8
+    for (int c = c0; c < c1; ++c) sum += chunkcount[(size_t)c * RADIX + d];
+    part[g][d] = sum;
+    __syncthreads();
+    u32 tot = 0, before = 0;
+    for (int q = 0; q < 4; ++q) { u32 v = part[q][d]; tot += v; if (q < g) before += v; }
+    u32 incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((d & 31) >= o) incl += t;
+    }
+    if (g == 0 && (d & 31) == 31) warp_tot[d >> 5] = incl;
+    __syncthreads();
+    u32 gb = incl - tot;
+    for (int w = 0; w < (d >> 5); ++w) gb += warp_tot[w];
+    if (g == 0) { totals[d] = tot; gbase[d] = gb; }
+    u32 run = gb + before;
+#pragma unroll 8
+    for (int c = c0; c < c1; ++c) {
+        u32 v = chunkcount[(size_t)c * RADIX + d];
+        segbase[(size_t)c * RADIX + d] = run;
+        run += v;
+    }
+}
+
+// Per-segment histograms of up to 4 digit functions over a segmented tile list (the histogram of a digit inside a
+// segment does not change while passes permute the items inside the segment: one read serves all of them).
+template <int WORDS, class DigitFn>
+__global__ void __launch_bounds__(512) seg_count_kernel(const typename ItemT<WORDS>::type* __restrict__ in, SegList sl,
+                                                        const DigitList<DigitFn> dl, u32* __restrict__ segcount /* [seg][n][RADIX] */) {
+    __shared__ u32 sh[4 * RADIX];
+    for (u32 j = blockIdx.x; j < sl.num_tiles; j += gridDim.x) {
+        const uint4 t = __ldg(&sl.tiles[j]);
+        for (int i = threadIdx.x; i < dl.n * RADIX; i += blockDim.x) sh[i] = 0;
+        __syncthreads();
+        for (u32 i = threadIdx.x; i < t.y; i += blockDim.x) {
+            const typename ItemT<WORDS>::type v = in[(size_t)t.x + i];
+            for (int p = 0; p < dl.n; ++p) atomicAdd(&sh[p * RADIX + dl.fn[p](v, t.x + i)], 1u);
+        }
+        __syncthreads();
+        u32* dst = segcount + (size_t)(t.w >> 20) * dl.n * RADIX;
+        for (int i = threadIdx.x; i < dl.n * RADIX; i += blockDim.x)
+            if (sh[i]) atomicAdd(&dst[i], sh[i]);
+        __syncthreads();
+    }
+}
+
+// segbase[pos][seg][d] = seg_start[seg] + exclusive scan over d of segcount[seg][pos][.]; grid (nseg, npos), RADIX threads
+static __global__ void seg_scan_kernel(const u32* __restrict__ segcount, const u32* __restrict__ seg_start, int npos, int nseg,
+                                       u32* __restrict__ segbase) {
+    __shared__ u32 warp_tot[RADIX / 32];
+    const int seg = blockIdx.x, pos = blockIdx.y, d = threadIdx.x;
+    const u32 c = segcount[((size_t)seg * npos + pos) * RADIX + d];
+    u32 incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((d & 31) >= o) incl += t;
+    }
+    if ((d & 31) == 31) warp_tot[d >> 5] = incl;
+    __syncthreads();
+    u32 add = seg_start[seg];
+    for (int w = 0; w < (d >> 5); ++w) add += warp_tot[w];
+    segbase[((size_t)pos * nseg + seg) * RADIX + d] = add + incl - c;
+}
+
+// Tile list of `nseg` segments of seg_size[] items laid out back to back, interleaving the segments: round r holds the
+// r-th tile of every segment that has one (so a tile's predecessor in its segment is a whole round away).  The list is
+// staged in pinned host memory (the previous list must have been consumed: callers synchronise the stream before) and
+// copied to *d_tiles (workspace slot `ws_slot`).
+inline int build_tile_list(tg_ctx* ctx, int nseg, const u32* seg_size, u32 tile, int ws_slot, uint4** d_tiles, u32* total_out) {
+    if (nseg > 4096) return tg_set_error(ctx, TG_ERR_ARG, "tile list: at most 4096 segments");
+    std::vector<u32> ntiles(nseg), row0(nseg), start(nseg), order(nseg);
+    u32 total = 0, acc = 0, maxt = 0;
+    for (int s = 0; s < nseg; ++s) {
+        ntiles[s] = (seg_size[s] + tile - 1) / tile;
+        row0[s] = total;
+        start[s] = acc;
+        total += ntiles[s];
+        acc += seg_size[s];
+        if (ntiles[s] > maxt) maxt = ntiles[s];
+        order[s] = (u32)s;
+    }
+    if (maxt >= (1u << 20)) return tg_set_error(ctx, TG_ERR_TOO_LARGE, "tile list: segment of %u tiles", maxt);
+    std::sort(order.begin(), order.end(), [&](u32 a, u32 b) { return ntiles[a] != ntiles[b] ? ntiles[a] > ntiles[b] : a < b; });
+    uint4* h_tiles;
+    TG_TRY(tg_pinned_list(ctx, (size_t)total * sizeof(uint4) + 16, (void**)&h_tiles));
+    u32 w = 0;
+    for (u32 r = 0; r < maxt; ++r) {
+        for (int o = 0; o < nseg; ++o) {
+            const u32 sg = order[o];
+            if (ntiles[sg] <= r) break;               // sorted by tile count: nobody further has a round r
+            const u32 off = r * tile;
+            const u32 len = seg_size[sg] - off < tile ? seg_size[sg] - off : tile;
+            h_tiles[w++] = make_uint4(start[sg] + off, len, row0[sg] + r, (sg << 20) | r);
+        }
+    }
+    TG_TRY(tg_ws_get(ctx, ws_slot, (size_t)total * sizeof(uint4) + 16, (void**)d_tiles));
+    if (total) TG_CUDA(ctx, cudaMemcpyAsync(*d_tiles, h_tiles, (size_t)total * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream));
+    *total_out = total;
+    return TG_OK;
+}
+
+// chunk geometry of a chunked pass over n items: ~2 chunks per SM, whole tiles
+struct ChunkGeom {
+    u32 chunk_items;
+    int nchunks;
+};
+template <int WORDS>
+inline ChunkGeom chunk_geometry(const tg_ctx* ctx, size_t n) {
+    const u32 tile = tile_items<WORDS>();
+    const u32 tiles_total = (u32)((n + tile - 1) / tile);
+    u32 want = (u32)ctx->sm_count * 2;
+    if (want > tiles_total) want = tiles_total;
+    if (want == 0) want = 1;
+    ChunkGeom g;
+    g.chunk_items = ((tiles_total + want - 1) / want) * tile;
+    if (g.chunk_items == 0) g.chunk_items = tile;
+    g.nchunks = (int)((n + g.chunk_items - 1) / g.chunk_items);
+    return g;
+}
+
+// Stand-alone stable partition of n items into <= RADIX buckets as a chunked pass (counting read, scan, pass): the
+// replacement of partition_items' chained scan.  *d_totals / *d_gbase (device, RADIX u32): bucket sizes and starts.
+// Uses the workspace slots WS_SORT_HIST2 (tables), WS_SEG_TILES2 (tile list), WS_SORT_STATUS (scan status).
+template <int WORDS, class DigitFn>
+int partition_chunked(tg_ctx* ctx, const void* in, void* out, size_t n, const DigitFn& fn, u32** d_totals, u32** d_gbase) {
+    typedef typename ItemT<WORDS>::type Item;
+    const ChunkGeom g = chunk_geometry<WORDS>(ctx, n);
+    const size_t cw = (size_t)(g.nchunks > 0 ? g.nchunks : 1) * RADIX;
+    u32* tab;
+    TG_TRY(tg_ws_get(ctx, WS_SORT_HIST2, (2 * cw + 2 * RADIX + 16) * 4, (void**)&tab));
+    u32* chunkcount = tab;
+    u32* chunkbase = tab + cw;
+    u32* totals = chunkbase + cw;
+    u32* gbase = totals + RADIX;
+    if (d_totals) *d_totals = totals;
+    if (d_gbase) *d_gbase = gbase;
+    if (n == 0) {
+        TG_CUDA(ctx, cudaMemsetAsync(totals, 0, 2 * RADIX * 4, ctx->stream));
+        return TG_OK;
+    }
+    TG_LAUNCH_T(ctx, TG_K_RADIX_HIST, (chunk_hist_kernel<WORDS, DigitFn, false>), g.nchunks, 512, 0, (const Item*)in, (u32)n,
+                g.chunk_items, fn, chunkcount, (u64*)nullptr);
+    TG_LAUNCH(ctx, chunk_scan_kernel, 1, 4 * RADIX, 0, chunkcount, g.nchunks, totals, gbase, chunkbase);
+    std::vector<u32> chunk_size(g.nchunks, g.chunk_items);
+    chunk_size[g.nchunks - 1] = (u32)(n - (size_t)(g.nchunks - 1) * g.chunk_items);
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));          // the pinned staging of an earlier list is free again
+    uint4* d_tiles;
+    u32 total = 0;
+    TG_TRY(build_tile_list(ctx, g.nchunks, chunk_size.data(), tile_items<WORDS>(), WS_SEG_TILES2, &d_tiles, &total));
+    u32* status;
+    TG_TRY(tg_ws_get(ctx, WS_SORT_STATUS, (size_t)total * RADIX * 4, (void**)&status));
+    TG_CUDA(ctx, cudaMemsetAsync(status, 0, (size_t)total * RADIX * 4, ctx->stream));
+    SegList sl = { d_tiles, chunkbase, total };
+    return launch_partition_seg<WORDS, DigitFn>(ctx, in, out, fn, status, sl);
+}
+
+}  // namespace tgp
