@@ -33,7 +33,7 @@ SORT_N_PER_GPU = 100000000
 REDUCE_N_PER_GPU = 125000000
 ZIPF_UNIVERSE = 1 << 26
 SORT_PASS_BYTES_PER_KEY = 16.0          # one onesweep pass: read 8 + write 8
-PREAGG_BYTES_PER_RECORD = 16.0          # pre phase reads every record once
+REDUCE_PASS_BYTES_PER_RECORD = 32.0     # one hash-digit partition pass: read 16 + write 16
 
 
 def measured_peaks():
@@ -247,6 +247,8 @@ def main():
     part_ms, part_cnt = tg.profile_get(capi.K_PARTITION)
     hist_ms, hist_cnt = tg.profile_get(capi.K_RADIX_HIST)
     merge_ms, merge_cnt = tg.profile_get(capi.K_MERGE)
+    fix_ms, fix_cnt = tg.profile_get(capi.K_FIXUP)
+    segc_ms, segc_cnt = tg.profile_get(capi.K_SEGCOUNT)
     tg.profile_enable(False)
     # cheap parity properties on the last result (outside the timed region)
     ok_sorted = tg.is_sorted(desc, out_p.value, out_n.value)
@@ -257,13 +259,16 @@ def main():
     value = n * world / (ms_per_step / 1e3)
     pass_launch_ms = part_ms / max(part_cnt, 1)
     achieved = SORT_PASS_BYTES_PER_KEY * n / (pass_launch_ms / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "tgp::partition_kernel<1,512,RadixDigit> (one 8-bit onesweep pass)",
+    roofline = {"bound": "hbm", "kernel": "tgp::partition_kernel<1,512,16,1,RadixDigit,SEG> (one stable 8-bit partition pass: "
+                                          "read 8 B + write 8 B per key)",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "peak_source": peak_src, "traffic": None,
                 "algorithmic_bytes_per_launch": SORT_PASS_BYTES_PER_KEY * n, "launch_ms": pass_launch_ms,
                 "launches_timed": part_cnt,
-                "step_share": {"partition_ms": part_ms / K, "radix_hist_ms": hist_ms / K, "merge_ms": merge_ms / K,
-                               "step_ms": ms_per_step}}
+                "step_share": {"partition_ms": part_ms / K, "partition_launches_per_step": part_cnt / K,
+                               "radix_hist_ms": hist_ms / K, "segment_count_ms": segc_ms / K, "finishing_pass_ms": fix_ms / K,
+                               "merge_ms": merge_ms / K, "step_ms": ms_per_step},
+                "prefix_sort_fallbacks": int(L.tg_prefix_sort_fallbacks(tg.h))}
 
     # ------------------------------------------------------------------ Sort, end to end (host Files) ---
     host_in = tg.host_alloc(n * 8)
@@ -310,21 +315,26 @@ def main():
             ms = max_over_ranks(tg.timer_stop(), world)
             if it >= 2:
                 r_ms.append(ms)
-        pre_ms, pre_cnt = tg.profile_get(capi.K_PREAGG)
         agg_ms, agg_cnt = tg.profile_get(capi.K_AGGREGATE)
         cmp_ms, cmp_cnt = tg.profile_get(capi.K_COMPACT)
         rpart_ms, rpart_cnt = tg.profile_get(capi.K_PARTITION)
+        rhist_ms, rhist_cnt = tg.profile_get(capi.K_RADIX_HIST)
+        rsegc_ms, rsegc_cnt = tg.profile_get(capi.K_SEGCOUNT)
         tg.profile_enable(False)
         r_step = sum(r_ms) / len(r_ms)
-        pre_launch = pre_ms / max(pre_cnt, 1)
-        r_ach = PREAGG_BYTES_PER_RECORD * rn / (pre_launch / 1e3) / 1e9
+        # dominant kernel: the stable partition pass over 16-byte records (the first two launches of a step move all
+        # rn records: read 16 + write 16 bytes each); later launches of a multi-GPU step move fewer
+        part_launch = rpart_ms / max(rpart_cnt, 1)
+        r_ach = REDUCE_PASS_BYTES_PER_RECORD * rn / (part_launch / 1e3) / 1e9 if world == 1 else None
         extra = {"reduce_records_per_s": rn * world / (r_step / 1e3), "reduce_ms_per_step": r_step,
                  "reduce_distinct_out": int(sum_over_ranks(float(rcount.value), world)),
                  "reduce_config": {"workload": "reduce_pair_u64_f64_zipf_s1_U2^26", "records_per_gpu": rn},
-                 "reduce_roofline": {"bound": "hbm", "kernel": "preagg_kernel", "achieved": r_ach, "peak": hbm_peak,
-                                     "unit": "GB/s", "frac": r_ach / hbm_peak, "launch_ms": pre_launch,
-                                     "step_share": {"preagg_ms": pre_ms / 3, "aggregate_ms": agg_ms / 3, "compact_ms": cmp_ms / 3,
-                                                    "partition_ms": rpart_ms / 3, "step_ms": r_step}}}
+                 "reduce_roofline": {"bound": "hbm", "kernel": "tgp::partition_kernel<2,512,8,1,HashLevelDigit,SEG> (one hash-digit pass)",
+                                     "achieved": r_ach, "peak": hbm_peak, "unit": "GB/s",
+                                     "frac": (r_ach / hbm_peak) if r_ach else None, "launch_ms": part_launch,
+                                     "step_share": {"partition_ms": rpart_ms / 3, "partition_launches_per_step": rpart_cnt / 3,
+                                                    "count_ms": (rhist_ms + rsegc_ms) / 3, "aggregate_ms": agg_ms / 3,
+                                                    "compact_ms": cmp_ms / 3, "step_ms": r_step}}}
         tg.free(d_rin); tg.free(d_cdf)
 
     clocks = sampler.stop()

@@ -130,3 +130,50 @@ def test_reduce_large_device_generated_exact(ctx):
     ref = O.reduce_simple(kv, O.OP_SUM_F64)
     assert np.array_equal(out, ref)
     ctx.free(d_in); ctx.free(d_cdf)
+
+
+@pytest.mark.parametrize("op", ["sum_u64", "min_u64", "max_u64", "sum_f64_exact", "min_f64", "max_f64"])
+def test_partitioned_aggregate_ops_hot_and_zero_keys(ctx, op):
+    """n above the threshold of the partitioned aggregation (two hash-digit passes + shared-memory tables): a hot key
+    whose segment is cut into several units (merged afterwards), the zero key (side slot), and a long tail."""
+    from thrill_b200 import capi
+    n = 700001
+    rng = np.random.RandomState(len(op))
+    kv = np.zeros(n, dtype=O.KV)
+    keys = rng.randint(1, 100000, size=n).astype(np.uint64)
+    sel = rng.rand(n)
+    keys[sel < 0.30] = 7                    # hot: ~210000 records = ~100 units
+    keys[(sel >= 0.30) & (sel < 0.40)] = 0  # the sentinel key
+    keys[(sel >= 0.40) & (sel < 0.45)] = 2**63 + 12345
+    kv["key"] = keys
+    if op.endswith("u64"):
+        kv["val"] = rng.randint(0, 1 << 40, size=n)
+    elif op == "sum_f64_exact":
+        kv["val"] = rng.randint(0, 1024, size=n).astype(np.float64).view(np.uint64)
+    else:
+        kv["val"] = (rng.rand(n) * 100 - 50).view(np.uint64)
+    code = {"sum_u64": capi.OP_SUM_U64, "min_u64": capi.OP_MIN_U64, "max_u64": capi.OP_MAX_U64,
+            "sum_f64_exact": capi.OP_SUM_F64, "min_f64": capi.OP_MIN_F64, "max_f64": capi.OP_MAX_F64}[op]
+    ocode = {"sum_u64": O.OP_SUM_U64, "min_u64": O.OP_MIN_U64, "max_u64": O.OP_MAX_U64,
+             "sum_f64_exact": O.OP_SUM_F64, "min_f64": O.OP_MIN_F64, "max_f64": O.OP_MAX_F64}[op]
+    out = _aggregate(ctx, kv, code)
+    ref = O.reduce_simple(kv, ocode)
+    assert np.array_equal(out, ref)
+
+
+def test_partitioned_aggregate_all_distinct_and_f64_tolerance(ctx):
+    """every key once (nothing to reduce, every segment full of distinct keys), then uniform duplicates with real
+    doubles: keys exact, sums within the stated tolerance"""
+    from thrill_b200 import capi
+    n = 1 << 20
+    kv = np.zeros(n, dtype=O.KV)
+    kv["key"] = np.random.RandomState(3).permutation(n).astype(np.uint64) * np.uint64(2654435761) + np.uint64(1)
+    kv["val"] = np.arange(n, dtype=np.uint64)
+    out = _aggregate(ctx, kv, capi.OP_SUM_U64)
+    assert np.array_equal(out, np.sort(kv, order="key"))
+    kv = O.gen_reduce_uniform(0, 900000, universe=1 << 17)
+    out = _aggregate(ctx, kv, capi.OP_SUM_F64)
+    ref = O.reduce_simple(kv, O.OP_SUM_F64)
+    assert np.array_equal(out["key"], ref["key"])
+    a, b = out["val"].view(np.float64), ref["val"].view(np.float64)
+    assert np.all(np.abs(a - b) <= F64_RTOL * np.maximum(1.0, np.abs(b)))

@@ -30,8 +30,8 @@ struct tg_ctx {
     size_t ws_bytes[TG_NUM_WS] = { 0 };
     void* pinned = nullptr;                     // small pinned staging area (control-plane scalars)
     size_t pinned_bytes = 0;
-    void* pinned_list = nullptr;                // pinned staging of host-built tile lists (tg_pinned_list)
-    size_t pinned_list_bytes = 0;
+    void* pinned_list[2] = { nullptr, nullptr };       // pinned staging of host-built tile / unit lists (tg_pinned_list)
+    size_t pinned_list_bytes[2] = { 0, 0 };
     // per-device kernel attributes already applied by this ctx (cudaFuncSetAttribute is per device, and one
     // process may drive several GPUs: Thrill runs its workers as threads): kernel -> resident CTAs per SM
     std::map<const void*, int> kernel_cfg;
@@ -58,7 +58,7 @@ enum { WS_SORT_TMP = 0, WS_SORT_STATUS = 1, WS_SORT_HIST = 2, WS_XCHG_SEND = 3, 
 
 int tg_set_error(tg_ctx* ctx, int status, const char* fmt, ...);
 int tg_ws_get(tg_ctx* ctx, int slot, size_t bytes, void** out);
-int tg_pinned_list(tg_ctx* ctx, size_t bytes, void** out);      // grown on demand, owned by the ctx
+int tg_pinned_list(tg_ctx* ctx, int which, size_t bytes, void** out);      // two buffers, grown on demand, owned by the ctx
 
 #define TG_CUDA(ctx, call)                                                                         \
     do {                                                                                           \

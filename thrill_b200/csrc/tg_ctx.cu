@@ -13,19 +13,19 @@ int tg_set_error(tg_ctx* ctx, int status, const char* fmt, ...) {
     return status;
 }
 
-int tg_pinned_list(tg_ctx* ctx, size_t bytes, void** out) {
-    if (ctx->pinned_list_bytes < bytes) {
-        if (ctx->pinned_list) {
+int tg_pinned_list(tg_ctx* ctx, int which, size_t bytes, void** out) {
+    if (ctx->pinned_list_bytes[which] < bytes) {
+        if (ctx->pinned_list[which]) {
             TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            TG_CUDA(ctx, cudaFreeHost(ctx->pinned_list));
-            ctx->pinned_list = nullptr;
-            ctx->pinned_list_bytes = 0;
+            TG_CUDA(ctx, cudaFreeHost(ctx->pinned_list[which]));
+            ctx->pinned_list[which] = nullptr;
+            ctx->pinned_list_bytes[which] = 0;
         }
         size_t want = bytes + (bytes >> 2) + 4096;
-        TG_CUDA(ctx, cudaMallocHost(&ctx->pinned_list, want));
-        ctx->pinned_list_bytes = want;
+        TG_CUDA(ctx, cudaMallocHost(&ctx->pinned_list[which], want));
+        ctx->pinned_list_bytes[which] = want;
     }
-    *out = ctx->pinned_list;
+    *out = ctx->pinned_list[which];
     return TG_OK;
 }
 
@@ -167,7 +167,7 @@ int tg_shutdown(tg_ctx* ctx) {
     for (int i = 0; i < TG_NUM_WS; ++i)
         if (ctx->ws[i]) cudaFree(ctx->ws[i]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
-    if (ctx->pinned_list) cudaFreeHost(ctx->pinned_list);
+    for (int i = 0; i < 2; ++i) if (ctx->pinned_list[i]) cudaFreeHost(ctx->pinned_list[i]);
     for (auto& e : ctx->prof_events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);

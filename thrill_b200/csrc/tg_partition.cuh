@@ -101,7 +101,8 @@ struct SweepCfg {
     static constexpr int TILE_BYTES = TILE * ITEM_BYTES;
     static constexpr int NWARPS = THREADS / 32;
     // 2 landing/exchange buffers | warp counters [NWARPS][RADIX] | goff [RADIX] | warp_tot [16] | mbar [2] | dig [TILE]
-    static constexpr int SMEM = 2 * TILE_BYTES + NWARPS * RADIX * 4 + RADIX * 4 + 64 + 16 + TILE + 256;
+    static constexpr int BUF_BYTES = TILE_BYTES + 16;       // + one 16-byte granule: tiles that start at an odd 8-byte item
+    static constexpr int SMEM = 2 * BUF_BYTES + NWARPS * RADIX * 4 + RADIX * 4 + 64 + 16 + TILE + 256;
 };
 
 // per-bucket counts of one digit function (the pre-pass of a stand-alone partition)
@@ -214,8 +215,8 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
     // plain pointer arithmetic on the shared array keeps the shared address space (LDS/STS, 32-bit addresses)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Item* const buf0 = reinterpret_cast<Item*>(smem_raw);
-    Item* const buf1 = reinterpret_cast<Item*>(smem_raw + C::TILE_BYTES);
-    u32* const whist = reinterpret_cast<u32*>(smem_raw + 2 * C::TILE_BYTES);     // [NWARPS][RADIX]
+    Item* const buf1 = reinterpret_cast<Item*>(smem_raw + C::BUF_BYTES);
+    u32* const whist = reinterpret_cast<u32*>(smem_raw + 2 * C::BUF_BYTES);      // [NWARPS][RADIX]
     u32* const goff = whist + NWARPS * RADIX;                                    // [RADIX]
     u32* const warp_tot = goff + RADIX;                                          // [16]
     u64* const mbar = reinterpret_cast<u64*>(warp_tot + 16);                     // [2]
@@ -244,8 +245,14 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
         }
         return ti;
     };
-    // a whole tile at a 16-byte aligned address is fetched by the TMA unit, anything else by ordinary loads
-    auto tma_ok = [&](const TileInfo& ti) -> bool { return ti.len == (u32)TILE && (((size_t)ti.start * sizeof(Item)) & 15) == 0; };
+    // A whole tile is fetched by the TMA unit (16-byte granules): a tile of 8-byte items that starts at an odd item is
+    // fetched from one item earlier, one granule longer (tma_shift = 1), if that stays inside the array; anything else
+    // by ordinary loads.
+    auto tma_shift = [&](const TileInfo& ti) -> u32 { return WORDS == 1 ? (ti.start & 1u) : 0u; };
+    auto tma_ok = [&](const TileInfo& ti) -> bool {
+        if (ti.len != (u32)TILE) return false;
+        return tma_shift(ti) == 0 || (size_t)ti.start + TILE + 1 <= n;
+    };
 
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
@@ -258,8 +265,9 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
     if (j < num_tiles) {
         const TileInfo t0 = tile_info(j);
         if (tid == 0 && tma_ok(t0)) {
-            mbar_expect_tx(&mbar[0], C::TILE_BYTES);
-            bulk_g2s(buf0, in + t0.start, C::TILE_BYTES, &mbar[0]);
+            const u32 sh = tma_shift(t0), bytes = C::TILE_BYTES + 16 * sh;
+            mbar_expect_tx(&mbar[0], bytes);
+            bulk_g2s(buf0, in + (t0.start - sh), bytes, &mbar[0]);
         }
     }
     u32 phase = 0;        // bit b: parity of the next completion of mbar[b]
@@ -279,9 +287,10 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
         if (tid == 0 && j + gridDim.x < num_tiles) {
             const TileInfo tn = tile_info(j + gridDim.x);
             if (tma_ok(tn)) {
+                const u32 sh = tma_shift(tn), bytes = C::TILE_BYTES + 16 * sh;
                 fence_proxy_async();
-                mbar_expect_tx(&mbar[cur ^ 1], C::TILE_BYTES);
-                bulk_g2s(nbuf, in + tn.start, C::TILE_BYTES, &mbar[cur ^ 1]);
+                mbar_expect_tx(&mbar[cur ^ 1], bytes);
+                bulk_g2s(nbuf, in + (tn.start - sh), bytes, &mbar[cur ^ 1]);
             }
         }
         // zero this warp's private digit counters
@@ -296,7 +305,7 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
         if (by_tma) {
             mbar_wait(&mbar[cur], (phase >> cur) & 1u);
             phase ^= 1u << cur;
-            const Item* src = buf + wbase + lane;
+            const Item* src = buf + tma_shift(ti) + wbase + lane;
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) key[i] = src[i * 32];
         }
@@ -537,18 +546,18 @@ inline u32 tile_items() {
     return (u32)v.threads * (u32)(v.wpt / WORDS);
 }
 
-// one partition pass over independent segments (see SegList); status = sl.num_tiles * RADIX zeroed words
+// one partition pass over independent segments (see SegList) of an array of n items; status = sl.num_tiles * RADIX zeroed words
 template <int WORDS, class DigitFn>
-int launch_partition_seg(tg_ctx* ctx, const void* in, void* out, const DigitFn& fn, u32* status, const SegList& sl) {
+int launch_partition_seg(tg_ctx* ctx, const void* in, void* out, u32 n, const DigitFn& fn, u32* status, const SegList& sl) {
     switch (sweep_cfg()) {
-    case 1: return launch_partition_v<WORDS, 256, 16, 2, DigitFn, true>(ctx, in, out, 0, fn, nullptr, status, sl);
-    case 2: return launch_partition_v<WORDS, 256, 16, 3, DigitFn, true>(ctx, in, out, 0, fn, nullptr, status, sl);
-    case 3: return launch_partition_v<WORDS, 384, 16, 2, DigitFn, true>(ctx, in, out, 0, fn, nullptr, status, sl);
-    case 4: return launch_partition_v<WORDS, 512, 8, 2, DigitFn, true>(ctx, in, out, 0, fn, nullptr, status, sl);
-    case 5: return launch_partition_v<WORDS, 256, 8, 4, DigitFn, true>(ctx, in, out, 0, fn, nullptr, status, sl);
-    case 6: return launch_partition_v<WORDS, 512, 8, 3, DigitFn, true>(ctx, in, out, 0, fn, nullptr, status, sl);
-    case 7: return launch_partition_v<WORDS, 1024, 8, 1, DigitFn, true>(ctx, in, out, 0, fn, nullptr, status, sl);
-    default: return launch_partition_v<WORDS, 512, 16, 1, DigitFn, true>(ctx, in, out, 0, fn, nullptr, status, sl);
+    case 1: return launch_partition_v<WORDS, 256, 16, 2, DigitFn, true>(ctx, in, out, n, fn, nullptr, status, sl);
+    case 2: return launch_partition_v<WORDS, 256, 16, 3, DigitFn, true>(ctx, in, out, n, fn, nullptr, status, sl);
+    case 3: return launch_partition_v<WORDS, 384, 16, 2, DigitFn, true>(ctx, in, out, n, fn, nullptr, status, sl);
+    case 4: return launch_partition_v<WORDS, 512, 8, 2, DigitFn, true>(ctx, in, out, n, fn, nullptr, status, sl);
+    case 5: return launch_partition_v<WORDS, 256, 8, 4, DigitFn, true>(ctx, in, out, n, fn, nullptr, status, sl);
+    case 6: return launch_partition_v<WORDS, 512, 8, 3, DigitFn, true>(ctx, in, out, n, fn, nullptr, status, sl);
+    case 7: return launch_partition_v<WORDS, 1024, 8, 1, DigitFn, true>(ctx, in, out, n, fn, nullptr, status, sl);
+    default: return launch_partition_v<WORDS, 512, 16, 1, DigitFn, true>(ctx, in, out, n, fn, nullptr, status, sl);
     }
 }
 

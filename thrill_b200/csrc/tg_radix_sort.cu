@@ -303,16 +303,15 @@ bool segmented_enabled() {
 // histogram of the digit the items are currently partitioned by (seg_size on the host, seg_start on the device)
 template <int WORDS>
 int run_segmented_passes(tg_ctx* ctx, const PassList& pl, const int* pos, int npos, const u32* seg_size,
-                         const u32* d_seg_start, void** src, void** dst) {
+                         const u32* d_seg_start, size_t n, void** src, void** dst) {
     typedef typename ItemT<WORDS>::type Item;
     if (npos == 0) return TG_OK;
     if (npos > 4) return tg_set_error(ctx, TG_ERR_ARG, "segmented passes: at most 4 digit positions");
-    // NOTE: the pinned staging buffer is reused by the next build_tile_list: the copy of this list must have been
-    // consumed (stream order) before the host overwrites it -> synchronise first
-    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // (pinned staging buffer 1: the chunk list of the pass before this may still be in flight from buffer 0; every caller
+    // has synchronised the stream since the previous use of buffer 1)
     uint4* d_tiles;
     u32 total = 0;
-    TG_TRY(build_tile_list(ctx, RADIX, seg_size, tile_items<WORDS>(), WS_SEG_TILES, &d_tiles, &total));
+    TG_TRY(build_tile_list(ctx, RADIX, seg_size, tile_items<WORDS>(), 1, WS_SEG_TILES, &d_tiles, &total));
     if (total == 0) return TG_OK;
     u32* tables;       // segcount [seg][npos][RADIX] | segbase [pos][seg][RADIX]
     const size_t table_words = (size_t)RADIX * npos * RADIX;
@@ -331,14 +330,12 @@ int run_segmented_passes(tg_ctx* ctx, const PassList& pl, const int* pos, int np
         const int q = pos[i < npos ? i : 0];
         dl.fn[i] = RadixDigit{ (int)pl.word[q], (int)pl.shift[q], pl.flip };
     }
-    int grid = ctx->sm_count * 4;
-    if ((u32)grid > total) grid = (int)total;
-    TG_LAUNCH_T(ctx, TG_K_SEGCOUNT, (seg_count_kernel<WORDS, RadixDigit>), grid, 512, 0, (const Item*)*src, sl, dl, segcount);
+    TG_TRY((launch_seg_count<WORDS, RadixDigit>(ctx, *src, sl, dl, segcount)));
     TG_LAUNCH(ctx, seg_scan_kernel, dim3(RADIX, npos), RADIX, 0, segcount, d_seg_start, npos, RADIX, segbase);
     for (int i = 0; i < npos; ++i) {
         RadixDigit fn = { (int)pl.word[pos[i]], (int)pl.shift[pos[i]], pl.flip };
         sl.segbase = segbase + (size_t)i * RADIX * RADIX;
-        TG_TRY((launch_partition_seg<WORDS, RadixDigit>(ctx, *src, *dst, fn, status + (size_t)i * pass_status_words, sl)));
+        TG_TRY((launch_partition_seg<WORDS, RadixDigit>(ctx, *src, *dst, (u32)n, fn, status + (size_t)i * pass_status_words, sl)));
         void* t = *src; *src = *dst; *dst = t;
     }
     return TG_OK;
@@ -409,7 +406,7 @@ int prefix_sort_fast(tg_ctx* ctx, const tg_key_desc* desc, const PassList& pl, b
     chunk_size[nchunks - 1] = (u32)(n - (size_t)(nchunks - 1) * chunk_items);
     uint4* d_ctiles;
     u32 ctotal = 0;
-    TG_TRY(build_tile_list(ctx, nchunks, chunk_size.data(), tile, WS_SEG_TILES2, &d_ctiles, &ctotal));
+    TG_TRY(build_tile_list(ctx, nchunks, chunk_size.data(), tile, 0, WS_SEG_TILES2, &d_ctiles, &ctotal));
     u32* cstatus;
     TG_TRY(tg_ws_get(ctx, WS_SORT_STATUS, (size_t)ctotal * RADIX * 4, (void**)&cstatus));
     TG_CUDA(ctx, cudaMemsetAsync(cstatus, 0, (size_t)ctotal * RADIX * 4, ctx->stream));
@@ -431,11 +428,11 @@ int prefix_sort_fast(tg_ctx* ctx, const tg_key_desc* desc, const PassList& pl, b
     {
         SegList sl = { d_ctiles, chunkbase, ctotal };
         RadixDigit fn = { (int)pl.word[top], (int)pl.shift[top], pl.flip };
-        TG_TRY((launch_partition_seg<WORDS, RadixDigit>(ctx, *src, *dst, fn, cstatus, sl)));
+        TG_TRY((launch_partition_seg<WORDS, RadixDigit>(ctx, *src, *dst, (u32)n, fn, cstatus, sl)));
         void* t = *src; *src = *dst; *dst = t;
     }
     // (2) the other K-1 prefix digits inside the buckets of (1)
-    TG_TRY((run_segmented_passes<WORDS>(ctx, pl, active + (nactive - K), K - 1, h_totals, gbase_top, src, dst)));
+    TG_TRY((run_segmented_passes<WORDS>(ctx, pl, active + (nactive - K), K - 1, h_totals, gbase_top, n, src, dst)));
     // (3) finishing pass
     bool ok = false;
     TG_TRY((run_fixup<WORDS>(ctx, desc, plain_u64, active[nactive - K], *src, *dst, n, fail, &ok)));
@@ -518,7 +515,7 @@ int radix_sort_impl(tg_ctx* ctx, const tg_key_desc* desc, const PassList& pl, vo
             // most significant digit first (global pass), then the other K-1 digits inside its buckets
             TG_TRY(run_pass(top));
             TG_TRY((run_segmented_passes<WORDS>(ctx, pl, active + (nactive - K), K - 1, h_hist + top * RADIX,
-                                                 gbase + (size_t)top * RADIX, &src, &dst)));
+                                                 gbase + (size_t)top * RADIX, n, &src, &dst)));
         }
         else
             for (int a = nactive - K; a < nactive; ++a) TG_TRY(run_pass(active[a]));

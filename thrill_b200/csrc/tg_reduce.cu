@@ -13,6 +13,9 @@
 //   exchange    : NCCL Alltoallv of the p contiguous groups                             (p > 1 only)
 //   post phase  : open-addressing table in HBM (16-byte slots, atomicCAS on the key, native atomics on the
 //                 value), sized from the number of partial aggregates, then compaction of the used slots
+#include <algorithm>
+#include <vector>
+
 #include "tg_partition.cuh"
 #include "tg_segmented.cuh"
 
@@ -371,6 +374,22 @@ __device__ __forceinline__ u64 op_combine(int op, u64 a, u64 b) {
     }
 }
 
+// reduce `v` over the lanes of `mask` (every lane of the warp calls it; lanes outside contribute the identity);
+// returns the total in every lane
+__device__ __forceinline__ u64 warp_reduce_masked(int op, u64 v, bool member, u64 ident) {
+    u64 x = member ? v : ident;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = op_combine(op, x, __shfl_xor_sync(0xffffffffu, x, o));
+    return x;
+}
+
+constexpr u32 AGG_MAX_UNIT = 1u << 16;             // longer segments are cut (their pieces are merged afterwards)
+constexpr u32 AGG_FLUSH_FILL = AGG_SLOTS * 3 / 4;  // the table is emitted early rather than filled beyond this
+
+// One unit = a run of records whose keys occur in no other unit (whole segments), or a piece of a very long segment
+// (`partial`: its aggregates are merged afterwards).  The unit is streamed through the table in rounds of AGG_UNIT
+// records; if the table would get too full it is emitted as partial aggregates and cleared (FlushPartition,
+// reduce_probing_hash_table.hpp:372-377).
 __global__ void __launch_bounds__(AGG_THREADS, 3)
 agg_units_kernel(const ulonglong2* __restrict__ in, const uint2* __restrict__ units /* {first record, records | partial << 31} */,
                  u32 nunits, int op, u64 ident, ulonglong2* __restrict__ out, u64* __restrict__ cursor,
@@ -379,62 +398,10 @@ agg_units_kernel(const ulonglong2* __restrict__ in, const uint2* __restrict__ un
     u64* const keys = reinterpret_cast<u64*>(agg_smem);
     u64* const vals = keys + AGG_SLOTS;
     u32* const scratch = reinterpret_cast<u32*>(vals + AGG_SLOTS);      // 36 words, 8-byte aligned
+    u32* const fill = scratch + 36;
     const u32 lane = lane_id();
-    for (u32 unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
-        const uint2 u = __ldg(&units[unit]);
-        const u32 start = u.x, len = u.y & 0x7fffffffu;
-        const bool partial = (u.y >> 31) != 0;
-        for (u32 i = threadIdx.x; i < AGG_SLOTS; i += AGG_THREADS) { keys[i] = 0; vals[i] = ident; }
-        __syncthreads();
-        u64 key[AGG_RPT], val[AGG_RPT];
-        bool valid[AGG_RPT];
-#pragma unroll
-        for (int r = 0; r < AGG_RPT; ++r) {
-            const u32 i = r * AGG_THREADS + threadIdx.x;
-            valid[r] = i < len;
-            ulonglong2 kv = valid[r] ? in[(size_t)start + i] : make_ulonglong2(0, 0);
-            key[r] = kv.x; val[r] = kv.y;
-        }
-#pragma unroll
-        for (int r = 0; r < AGG_RPT; ++r) {
-            // a warp whose 32 records carry the same key (a hot key's segment) reduces them in registers first
-            const u64 k0 = __shfl_sync(0xffffffffu, key[r], 0);
-            const bool uniform = __all_sync(0xffffffffu, valid[r] && key[r] == k0);
-            u64 v = val[r];
-            bool mine = valid[r];
-            if (uniform) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    // lower lane = earlier record: keeps TG_OP_FIRST's "first"
-                    u64 other = __shfl_down_sync(0xffffffffu, v, o);
-                    v = op_combine(op, v, other);
-                }
-                mine = lane == 0;
-            }
-            if (!mine) continue;
-            if (key[r] == 0) {
-                // Key() == 0: reduced in a side slot, never probed (reduce_probing_hash_table.hpp:195-218)
-                u64 prev = atomicCAS(&zero_slot[0], 0ull, 1ull);
-                op_apply(op, &zero_slot[1], v, prev == 0);
-                continue;
-            }
-            u32 slot = (u32)(key_hash(key[r]) >> AGG_SHIFT_SLOT) & (AGG_SLOTS - 1);
-            bool claimed = false;
-            while (true) {
-                u64 k = *(volatile u64*)&keys[slot];
-                if (k == 0) {
-                    k = atomicCAS(&keys[slot], 0ull, key[r]);
-                    claimed = k == 0;
-                    if (claimed) break;
-                }
-                if (k == key[r]) break;
-                slot = (slot + 1) & (AGG_SLOTS - 1);
-            }
-            op_apply(op, &vals[slot], v, claimed);
-        }
-        __syncthreads();
-        // emit the table (FlushPartitionEmit, reduce_probing_hash_table.hpp:443-482)
-        constexpr int EI = AGG_SLOTS / AGG_THREADS;
+    constexpr int EI = AGG_SLOTS / AGG_THREADS;
+    auto emit_table = [&](bool partial) {
         u64 ek[EI], ev[EI];
         bool has[EI];
 #pragma unroll
@@ -445,6 +412,81 @@ agg_units_kernel(const ulonglong2* __restrict__ in, const uint2* __restrict__ un
         }
         if (partial) emit_block<EI>(dup_out, dup_cursor, ek, ev, has, scratch);
         else emit_block<EI>(out, cursor, ek, ev, has, scratch);
+    };
+    auto clear_table = [&]() {
+        for (u32 i = threadIdx.x; i < AGG_SLOTS; i += AGG_THREADS) { keys[i] = 0; vals[i] = ident; }
+        if (threadIdx.x == 0) *fill = 0;
+        __syncthreads();
+    };
+    for (u32 unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+        const uint2 u = __ldg(&units[unit]);
+        const u32 start = u.x, len = u.y & 0x7fffffffu;
+        bool partial = (u.y >> 31) != 0;
+        clear_table();
+        for (u32 off = 0; off < len; off += AGG_UNIT) {
+            // every thread reads the fill count of the finished rounds between two barriers: a uniform decision
+            const u32 filled = *(volatile u32*)fill;
+            __syncthreads();
+            const u32 rlen = len - off < (u32)AGG_UNIT ? len - off : (u32)AGG_UNIT;
+            if (off && filled + rlen > AGG_FLUSH_FILL) {       // this round could take the table beyond 3/4 full
+                emit_table(true);
+                partial = true;
+                clear_table();
+            }
+            u64 key[AGG_RPT], val[AGG_RPT];
+            bool valid[AGG_RPT];
+#pragma unroll
+            for (int r = 0; r < AGG_RPT; ++r) {
+                const u32 i = r * AGG_THREADS + threadIdx.x;
+                valid[r] = i < rlen;
+                ulonglong2 kv = valid[r] ? in[(size_t)start + off + i] : make_ulonglong2(0, 0);
+                key[r] = kv.x; val[r] = kv.y;
+            }
+#pragma unroll
+            for (int r = 0; r < AGG_RPT; ++r) {
+                // Records of a popular key sit next to each other here (their segment holds little else): when at least a
+                // quarter of the warp carries the key of lane 0 (or of lane 16), those lanes are reduced in registers and one
+                // lane touches the table — 32 lanes spinning on one shared-memory CAS loop is the slow case.
+                u64 v = val[r];
+                bool mine = valid[r];
+#pragma unroll
+                for (int cand = 0; cand < 32; cand += 16) {
+                    const u64 kc = __shfl_sync(0xffffffffu, key[r], cand);
+                    const bool member = mine && key[r] == kc;
+                    const u32 mask = __ballot_sync(0xffffffffu, member);
+                    if (__popc(mask) >= 8) {
+                        u64 tot = (op == TG_OP_FIRST) ? __shfl_sync(0xffffffffu, v, __ffs(mask) - 1)
+                                                      : warp_reduce_masked(op, v, member, ident);
+                        if (member) {
+                            mine = lane == (u32)(__ffs(mask) - 1);
+                            v = tot;
+                        }
+                    }
+                }
+                if (!mine) continue;
+                if (key[r] == 0) {
+                    // Key() == 0: reduced in a side slot, never probed (reduce_probing_hash_table.hpp:195-218)
+                    u64 prev = atomicCAS(&zero_slot[0], 0ull, 1ull);
+                    op_apply(op, &zero_slot[1], v, prev == 0);
+                    continue;
+                }
+                u32 slot = (u32)(key_hash(key[r]) >> AGG_SHIFT_SLOT) & (AGG_SLOTS - 1);
+                bool claimed = false;
+                while (true) {
+                    u64 k = *(volatile u64*)&keys[slot];
+                    if (k == 0) {
+                        k = atomicCAS(&keys[slot], 0ull, key[r]);
+                        claimed = k == 0;
+                        if (claimed) { atomicAdd(fill, 1u); break; }
+                    }
+                    if (k == key[r]) break;
+                    slot = (slot + 1) & (AGG_SLOTS - 1);
+                }
+                op_apply(op, &vals[slot], v, claimed);
+            }
+            __syncthreads();
+        }
+        emit_table(partial);
         __syncthreads();
     }
 }
@@ -469,7 +511,7 @@ int run_partitioned_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 n, void
     // (2) second hash digit inside the buckets of the first: segmented pass
     uint4* d_tiles;
     u32 total = 0;
-    TG_TRY(build_tile_list(ctx, RADIX, h_tot1, tile_items<2>(), WS_SEG_TILES, &d_tiles, &total));
+    TG_TRY(build_tile_list(ctx, RADIX, h_tot1, tile_items<2>(), 1, WS_SEG_TILES, &d_tiles, &total));
     u32* tables;       // segcount [seg][RADIX] | segbase [seg][RADIX]
     const size_t table_words = (size_t)RADIX * RADIX;
     TG_TRY(tg_ws_get(ctx, WS_SEG_TABLES, 2 * table_words * 4, (void**)&tables));
@@ -483,37 +525,41 @@ int run_partitioned_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 n, void
     DigitList<HashLevelDigit> dl;
     dl.n = 1;
     for (int i = 0; i < 4; ++i) dl.fn[i] = HashLevelDigit{ AGG_SHIFT2 };
-    int grid = ctx->sm_count * 4;
-    if ((u32)grid > total) grid = (int)total;
-    TG_LAUNCH_T(ctx, TG_K_SEGCOUNT, (seg_count_kernel<2, HashLevelDigit>), grid, 512, 0, (const ulonglong2*)bufA, sl, dl, segcount);
+    TG_TRY((launch_seg_count<2, HashLevelDigit>(ctx, bufA, sl, dl, segcount)));
     TG_LAUNCH(ctx, seg_scan_kernel, dim3(RADIX, 1), RADIX, 0, segcount, d_gbase1, 1, RADIX, segbase);
-    TG_TRY((launch_partition_seg<2, HashLevelDigit>(ctx, bufA, bufB, dl.fn[0], status, sl)));
+    TG_TRY((launch_partition_seg<2, HashLevelDigit>(ctx, bufA, bufB, (u32)n, dl.fn[0], status, sl)));
     // (3) units: whole consecutive segments up to AGG_UNIT records; longer segments in pieces (partial)
     u32* h_seg;
-    TG_TRY(tg_pinned_list(ctx, table_words * 4 + (size_t)(n / AGG_UNIT + 2 * table_words + 16) * sizeof(uint2), (void**)&h_seg));
-    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));          // (the tile list staged in the same pinned buffer is consumed)
+    TG_TRY(tg_pinned_list(ctx, 0, table_words * 4 + (size_t)(n / AGG_UNIT + 3 * table_words + 16) * sizeof(uint2), (void**)&h_seg));
     TG_CUDA(ctx, cudaMemcpyAsync(h_seg, segcount, table_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
     TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // whole consecutive segments up to AGG_UNIT records share a unit; a longer segment is a unit of its own (streamed through
+    // the table in rounds), cut into partial pieces beyond AGG_MAX_UNIT records; long units first (static round robin)
     uint2* h_units = (uint2*)(h_seg + table_words);
+    std::vector<uint2> small_units;
     u32 nunits = 0, pos = 0, ustart = 0, ulen = 0;
     for (size_t sgi = 0; sgi < table_words; ++sgi) {
         const u32 c = h_seg[sgi];
         if (c == 0) continue;
         if (c > (u32)AGG_UNIT) {
-            if (ulen) { h_units[nunits++] = make_uint2(ustart, ulen); ulen = 0; }
-            for (u32 off = 0; off < c; off += AGG_UNIT) {
-                u32 l = c - off < (u32)AGG_UNIT ? c - off : (u32)AGG_UNIT;
-                h_units[nunits++] = make_uint2(pos + off, l | 0x80000000u);
-            }
+            if (ulen) { small_units.push_back(make_uint2(ustart, ulen)); ulen = 0; }
+            if (c <= AGG_MAX_UNIT) h_units[nunits++] = make_uint2(pos, c);
+            else
+                for (u32 off = 0; off < c; off += AGG_MAX_UNIT) {
+                    u32 l = c - off < AGG_MAX_UNIT ? c - off : AGG_MAX_UNIT;
+                    h_units[nunits++] = make_uint2(pos + off, l | 0x80000000u);
+                }
         }
         else {
-            if (ulen + c > (u32)AGG_UNIT) { h_units[nunits++] = make_uint2(ustart, ulen); ulen = 0; }
+            if (ulen + c > (u32)AGG_UNIT) { small_units.push_back(make_uint2(ustart, ulen)); ulen = 0; }
             if (ulen == 0) ustart = pos;
             ulen += c;
         }
         pos += c;
     }
-    if (ulen) h_units[nunits++] = make_uint2(ustart, ulen);
+    if (ulen) small_units.push_back(make_uint2(ustart, ulen));
+    std::sort(h_units, h_units + nunits, [](const uint2& a, const uint2& b) { return (a.y & 0x7fffffffu) > (b.y & 0x7fffffffu); });
+    for (const uint2& su : small_units) h_units[nunits++] = su;
     if (pos != (u32)n) return tg_set_error(ctx, TG_ERR_CUDA, "reduce: segment sizes add up to %u of %llu records", pos, (unsigned long long)n);
     uint2* d_units;
     TG_TRY(tg_ws_get(ctx, WS_SEG_TILES2, (size_t)nunits * sizeof(uint2) + 16, (void**)&d_units));
@@ -524,7 +570,7 @@ int run_partitioned_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 n, void
     ulonglong2* d_dup = (ulonglong2*)bufA;                     // the first pass's output is dead: reuse it for the partial aggregates
     int agrid = ctx->sm_count * 3;
     if ((u32)agrid > nunits) agrid = (int)nunits;
-    constexpr int AGG_SMEM = AGG_SLOTS * 16 + 36 * 4 + 16;
+    constexpr int AGG_SMEM = AGG_SLOTS * 16 + 36 * 4 + 32;
     if (ctx->kernel_cfg.find((const void*)agg_units_kernel) == ctx->kernel_cfg.end()) {
         TG_CUDA(ctx, cudaFuncSetAttribute(agg_units_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AGG_SMEM));
         ctx->kernel_cfg[(const void*)agg_units_kernel] = 3;

@@ -120,24 +120,55 @@ static __global__ void __launch_bounds__(4 * RADIX) chunk_scan_kernel(const u32*
 
 // Per-segment histograms of up to 4 digit functions over a segmented tile list (the histogram of a digit inside a
 // segment does not change while passes permute the items inside the segment: one read serves all of them).
-template <int WORDS, class DigitFn>
+template <int WORDS, class DigitFn, int NPOS>
 __global__ void __launch_bounds__(512) seg_count_kernel(const typename ItemT<WORDS>::type* __restrict__ in, SegList sl,
-                                                        const DigitList<DigitFn> dl, u32* __restrict__ segcount /* [seg][n][RADIX] */) {
-    __shared__ u32 sh[4 * RADIX];
+                                                        const DigitList<DigitFn> dl, u32* __restrict__ segcount /* [seg][NPOS][RADIX] */) {
+    typedef typename ItemT<WORDS>::type Item;
+    __shared__ u32 sh[NPOS * RADIX];
+    constexpr int U = 4;
     for (u32 j = blockIdx.x; j < sl.num_tiles; j += gridDim.x) {
         const uint4 t = __ldg(&sl.tiles[j]);
-        for (int i = threadIdx.x; i < dl.n * RADIX; i += blockDim.x) sh[i] = 0;
+        for (int i = threadIdx.x; i < NPOS * RADIX; i += blockDim.x) sh[i] = 0;
         __syncthreads();
-        for (u32 i = threadIdx.x; i < t.y; i += blockDim.x) {
-            const typename ItemT<WORDS>::type v = in[(size_t)t.x + i];
-            for (int p = 0; p < dl.n; ++p) atomicAdd(&sh[p * RADIX + dl.fn[p](v, t.x + i)], 1u);
+        for (u32 base = 0; base < t.y; base += blockDim.x * U) {
+            Item v[U];
+            bool valid[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const u32 i = base + u * blockDim.x + threadIdx.x;
+                valid[u] = i < t.y;
+                if (valid[u]) v[u] = in[(size_t)t.x + i];
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (!valid[u]) continue;
+#pragma unroll
+                for (int p = 0; p < NPOS; ++p) atomicAdd(&sh[p * RADIX + dl.fn[p](v[u], t.x + base + u * blockDim.x + threadIdx.x)], 1u);
+            }
         }
         __syncthreads();
-        u32* dst = segcount + (size_t)(t.w >> 20) * dl.n * RADIX;
-        for (int i = threadIdx.x; i < dl.n * RADIX; i += blockDim.x)
+        u32* dst = segcount + (size_t)(t.w >> 20) * NPOS * RADIX;
+        for (int i = threadIdx.x; i < NPOS * RADIX; i += blockDim.x)
             if (sh[i]) atomicAdd(&dst[i], sh[i]);
         __syncthreads();
     }
+}
+
+// launches seg_count_kernel for dl.n = 1..4 digit functions
+template <int WORDS, class DigitFn>
+int launch_seg_count(tg_ctx* ctx, const void* in, const SegList& sl, const DigitList<DigitFn>& dl, u32* segcount) {
+    typedef typename ItemT<WORDS>::type Item;
+    int grid = ctx->sm_count * 4;
+    if ((u32)grid > sl.num_tiles) grid = (int)sl.num_tiles;
+    if (grid == 0) return TG_OK;
+    switch (dl.n) {
+    case 1: TG_LAUNCH_T(ctx, TG_K_SEGCOUNT, (seg_count_kernel<WORDS, DigitFn, 1>), grid, 512, 0, (const Item*)in, sl, dl, segcount); break;
+    case 2: TG_LAUNCH_T(ctx, TG_K_SEGCOUNT, (seg_count_kernel<WORDS, DigitFn, 2>), grid, 512, 0, (const Item*)in, sl, dl, segcount); break;
+    case 3: TG_LAUNCH_T(ctx, TG_K_SEGCOUNT, (seg_count_kernel<WORDS, DigitFn, 3>), grid, 512, 0, (const Item*)in, sl, dl, segcount); break;
+    case 4: TG_LAUNCH_T(ctx, TG_K_SEGCOUNT, (seg_count_kernel<WORDS, DigitFn, 4>), grid, 512, 0, (const Item*)in, sl, dl, segcount); break;
+    default: return tg_set_error(ctx, TG_ERR_ARG, "segment count: %d digit functions", dl.n);
+    }
+    return TG_OK;
 }
 
 // segbase[pos][seg][d] = seg_start[seg] + exclusive scan over d of segcount[seg][pos][.]; grid (nseg, npos), RADIX threads
@@ -161,9 +192,9 @@ static __global__ void seg_scan_kernel(const u32* __restrict__ segcount, const u
 
 // Tile list of `nseg` segments of seg_size[] items laid out back to back, interleaving the segments: round r holds the
 // r-th tile of every segment that has one (so a tile's predecessor in its segment is a whole round away).  The list is
-// staged in pinned host memory (the previous list must have been consumed: callers synchronise the stream before) and
-// copied to *d_tiles (workspace slot `ws_slot`).
-inline int build_tile_list(tg_ctx* ctx, int nseg, const u32* seg_size, u32 tile, int ws_slot, uint4** d_tiles, u32* total_out) {
+// staged in pinned host buffer `stage` (0/1; the list staged there before must have been consumed by its copy: callers
+// alternate the two buffers between stream synchronisations) and copied to *d_tiles (workspace slot `ws_slot`).
+inline int build_tile_list(tg_ctx* ctx, int nseg, const u32* seg_size, u32 tile, int stage, int ws_slot, uint4** d_tiles, u32* total_out) {
     if (nseg > 4096) return tg_set_error(ctx, TG_ERR_ARG, "tile list: at most 4096 segments");
     std::vector<u32> ntiles(nseg), row0(nseg), start(nseg), order(nseg);
     u32 total = 0, acc = 0, maxt = 0;
@@ -179,7 +210,7 @@ inline int build_tile_list(tg_ctx* ctx, int nseg, const u32* seg_size, u32 tile,
     if (maxt >= (1u << 20)) return tg_set_error(ctx, TG_ERR_TOO_LARGE, "tile list: segment of %u tiles", maxt);
     std::sort(order.begin(), order.end(), [&](u32 a, u32 b) { return ntiles[a] != ntiles[b] ? ntiles[a] > ntiles[b] : a < b; });
     uint4* h_tiles;
-    TG_TRY(tg_pinned_list(ctx, (size_t)total * sizeof(uint4) + 16, (void**)&h_tiles));
+    TG_TRY(tg_pinned_list(ctx, stage, (size_t)total * sizeof(uint4) + 16, (void**)&h_tiles));
     u32 w = 0;
     for (u32 r = 0; r < maxt; ++r) {
         for (int o = 0; o < nseg; ++o) {
@@ -243,12 +274,12 @@ int partition_chunked(tg_ctx* ctx, const void* in, void* out, size_t n, const Di
     TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));          // the pinned staging of an earlier list is free again
     uint4* d_tiles;
     u32 total = 0;
-    TG_TRY(build_tile_list(ctx, g.nchunks, chunk_size.data(), tile_items<WORDS>(), WS_SEG_TILES2, &d_tiles, &total));
+    TG_TRY(build_tile_list(ctx, g.nchunks, chunk_size.data(), tile_items<WORDS>(), 0, WS_SEG_TILES2, &d_tiles, &total));
     u32* status;
     TG_TRY(tg_ws_get(ctx, WS_SORT_STATUS, (size_t)total * RADIX * 4, (void**)&status));
     TG_CUDA(ctx, cudaMemsetAsync(status, 0, (size_t)total * RADIX * 4, ctx->stream));
     SegList sl = { d_tiles, chunkbase, total };
-    return launch_partition_seg<WORDS, DigitFn>(ctx, in, out, fn, status, sl);
+    return launch_partition_seg<WORDS, DigitFn>(ctx, in, out, (u32)n, fn, status, sl);
 }
 
 }  // namespace tgp
