@@ -620,7 +620,7 @@ int tg_hash_partition(tg_ctx* ctx, const tg_kv_desc* desc, const void* d_in, siz
     TG_CUDA(ctx, cudaSetDevice(ctx->device));
     HashDigit fn = { p };
     u32* d_counts = nullptr;
-    TG_TRY((partition_items<2, HashDigit>(ctx, d_in, d_out, (u32)n, fn, &d_counts)));
+    TG_TRY((partition_chunked<2, HashDigit>(ctx, d_in, d_out, n, fn, &d_counts, nullptr)));
     u32* hc = (u32*)ctx->pinned;
     TG_CUDA(ctx, cudaMemcpyAsync(hc, d_counts, RADIX * 4, cudaMemcpyDeviceToHost, ctx->stream));
     TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -654,7 +654,7 @@ int tg_reduce_by_key(tg_ctx* ctx, const tg_kv_desc* desc, const void* d_in, size
         TG_TRY(tg_ws_get(ctx, WS_XCHG_SEND, (m + 2) * 16, &d_send));
         HashDigit fn = { (u32)p };
         u32* d_counts = nullptr;
-        TG_TRY((partition_items<2, HashDigit>(ctx, d_pre, d_send, (u32)m, fn, &d_counts)));
+        TG_TRY((partition_chunked<2, HashDigit>(ctx, d_pre, d_send, m, fn, &d_counts, nullptr)));
         u32* hc = (u32*)ctx->pinned;
         TG_CUDA(ctx, cudaMemcpyAsync(hc, d_counts, RADIX * 4, cudaMemcpyDeviceToHost, ctx->stream));
         TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

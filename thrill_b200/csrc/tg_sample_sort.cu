@@ -17,6 +17,7 @@
 
 #include "tg_partition.cuh"
 #include "tg_keys.cuh"
+#include "tg_segmented.cuh"
 
 using namespace tgp;
 
@@ -225,6 +226,14 @@ void canon_splitters_from_packed(const tg_key_desc* desc, const KeyView& kv, con
     }
 }
 
+// order of the multi-worker pipeline: classify/scatter -> exchange -> sort (default, the reference's order), or
+// TG_SORT_PIPELINE=merge: sort -> boundaries -> exchange -> merge of the received runs
+bool classify_first() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("TG_SORT_PIPELINE"); v = (e && !strcmp(e, "merge")) ? 0 : 1; }
+    return v != 0;
+}
+
 // splitters[i-1] = samples[(size_t)(i * double(S)/double(p))] over the (key, index)-sorted samples
 // (api/sort.hpp:357-372)
 void pick_splitters(std::vector<CanonIdx>& samples, uint32_t p, std::vector<CanonIdx>* spl) {
@@ -279,6 +288,49 @@ int sort_multi_impl(tg_ctx* ctx, const tg_key_desc* desc, const KeyView& kv, voi
         for (u32 i = 0; i < ns_of[r]; ++i) samples.push_back(all[(size_t)r * max_s + i]);
     pick_splitters(samples, (uint32_t)p, &spl);      // identical on every rank (same data, same order)
     const u32 nspl = (u32)spl.size();
+
+    if (classify_first()) {
+        // The reference's own order (api/sort.hpp:615-742): classify + scatter by the splitters (TransmitItems), exchange, then
+        // sort what was received.  One partition pass and one local sort instead of a local sort and ceil(log2 p) merge levels.
+        CanonIdx* d_splc = d_samp;
+        TG_CUDA(ctx, cudaMemcpyAsync(d_splc, spl.data(), nspl * sizeof(CanonIdx), cudaMemcpyHostToDevice, ctx->stream));
+        SplitterDigit fn = { d_splc, nspl, prefix, kv };
+        void* d_part;
+        TG_TRY(tg_ws_get(ctx, WS_XCHG_SEND, (n_local + 1) * s, &d_part));
+        u32 *d_tot = nullptr, *d_gb = nullptr;
+        TG_TRY((partition_chunked<WORDS, SplitterDigit>(ctx, d_in, d_part, n_local, fn, &d_tot, &d_gb)));
+        u32* hc = (u32*)ctx->pinned;
+        TG_CUDA(ctx, cudaMemcpyAsync(hc, d_tot, RADIX * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        std::vector<u64> send_cnt(p), send_off(p + 1, 0);
+        for (int r = 0; r < p; ++r) { send_cnt[r] = hc[r]; send_off[r + 1] = send_off[r] + send_cnt[r]; }
+        for (int r = 0; r < p; ++r) h[r] = send_cnt[r];
+        TG_CUDA(ctx, cudaMemcpyAsync(d_ctl, h, 8 * p, cudaMemcpyHostToDevice, ctx->stream));
+        TG_NCCL(ctx, ncclAllGather(d_ctl, d_ctl + 64, p, ncclUint64, ctx->comm, ctx->stream));
+        TG_CUDA(ctx, cudaMemcpyAsync(h, d_ctl + 64, 8 * p * p, cudaMemcpyDeviceToHost, ctx->stream));
+        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        std::vector<u64> recv_cnt(p), recv_off(p + 1, 0);
+        for (int r = 0; r < p; ++r) { recv_cnt[r] = h[(size_t)r * p + me]; recv_off[r + 1] = recv_off[r] + recv_cnt[r]; }
+        const u64 n_recv = recv_off[p];
+        if (n_recv >= (1u << 30)) return tg_set_error(ctx, TG_ERR_TOO_LARGE, "sort: %llu items received", (unsigned long long)n_recv);
+        Item* d_recv;
+        TG_TRY(tg_ws_get(ctx, WS_XCHG_RECV, (n_recv + 2) * s, (void**)&d_recv));
+        TG_NCCL(ctx, ncclGroupStart());
+        for (int r = 0; r < p; ++r) {
+            if (send_cnt[r]) TG_NCCL(ctx, ncclSend((const Item*)d_part + send_off[r], send_cnt[r] * s, ncclUint8, r, ctx->comm, ctx->stream));
+            if (recv_cnt[r]) TG_NCCL(ctx, ncclRecv(d_recv + recv_off[r], recv_cnt[r] * s, ncclUint8, r, ctx->comm, ctx->stream));
+        }
+        TG_NCCL(ctx, ncclGroupEnd());
+        // ReceiveItems + SortAndWriteToFile (:665-742): the received items arrive grouped by source worker in worker order, each
+        // group in input order: the stable local sort leaves equal keys in global input order
+        void* d_tmp2;
+        TG_TRY(tg_ws_get(ctx, WS_SORT_TMP, (n_recv + 2) * s, &d_tmp2));
+        void* d_res = d_recv;
+        TG_TRY(tg_radix_sort_items(ctx, desc, d_recv, d_tmp2, n_recv, &d_res));
+        *out_dptr = d_res;
+        *out_n = (size_t)n_recv;
+        return TG_OK;
+    }
 
     // (3) per-splitter tie counts on the unsorted shard, (4) local radix sort, (5) bucket boundaries
     CanonIdx* d_spl = d_samp;       // reuse
@@ -567,8 +619,8 @@ int tg_classify_scatter(tg_ctx* ctx, const tg_key_desc* desc, const void* d_in, 
     if (p > 1) TG_CUDA(ctx, cudaMemcpyAsync(d_spl, spl.data(), (p - 1) * sizeof(CanonIdx), cudaMemcpyHostToDevice, ctx->stream));
     SplitterDigit fn = { d_spl, p - 1, global_index_base, kv };
     u32* d_counts = nullptr;
-    if (desc->item_bytes == 8) TG_TRY((partition_items<1, SplitterDigit>(ctx, d_in, d_out, (u32)n, fn, &d_counts)));
-    else TG_TRY((partition_items<2, SplitterDigit>(ctx, d_in, d_out, (u32)n, fn, &d_counts)));
+    if (desc->item_bytes == 8) TG_TRY((partition_chunked<1, SplitterDigit>(ctx, d_in, d_out, n, fn, &d_counts, nullptr)));
+    else TG_TRY((partition_chunked<2, SplitterDigit>(ctx, d_in, d_out, n, fn, &d_counts, nullptr)));
     u32* hc = (u32*)ctx->pinned;
     TG_CUDA(ctx, cudaMemcpyAsync(hc, d_counts, RADIX * 4, cudaMemcpyDeviceToHost, ctx->stream));
     TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
