@@ -93,7 +93,7 @@ __device__ __forceinline__ u32 match_digit8(u32 d) {
 }
 
 // tile geometry of one launch configuration: THREADS threads, each owning IPT items of WORDS 8-byte words
-template <int WORDS, int THREADS, int IPT>
+template <int WORDS, int THREADS, int IPT, bool TMA = true>
 struct SweepCfg {
     static constexpr int ITEM_BYTES = 8 * WORDS;
     static constexpr int ITEMS = IPT;
@@ -102,7 +102,8 @@ struct SweepCfg {
     static constexpr int NWARPS = THREADS / 32;
     // 2 landing/exchange buffers | warp counters [NWARPS][RADIX] | goff [RADIX] | warp_tot [16] | mbar [2] | dig [TILE]
     static constexpr int BUF_BYTES = TILE_BYTES + 16;       // + one 16-byte granule: tiles that start at an odd 8-byte item
-    static constexpr int SMEM = 2 * BUF_BYTES + NWARPS * RADIX * 4 + RADIX * 4 + 64 + 16 + TILE + 256;
+    static constexpr int NBUF = TMA ? 2 : 1;                // landing + exchange, or the exchange buffer alone
+    static constexpr int SMEM = NBUF * BUF_BYTES + NWARPS * RADIX * 4 + RADIX * 4 + 64 + 16 + TILE + 256;
 };
 
 // per-bucket counts of one digit function (the pre-pass of a stand-alone partition)
@@ -198,7 +199,7 @@ struct SegList {
 
 // One tile: rank -> per-digit counts (published for the chained scan) -> scatter into the exchange buffer while
 // the look-back loads are in flight -> resolve the look-back -> coalesced write-out.
-template <int WORDS, int THREADS, int IPT, int MINB, class DigitFn, bool SEG, bool DBG = false>
+template <int WORDS, int THREADS, int IPT, int MINB, class DigitFn, bool SEG, bool DBG = false, bool TMA = true>
 __global__ void __launch_bounds__(THREADS, MINB)
 partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename ItemT<WORDS>::type* __restrict__ out,
                  u32 n, const DigitFn fn_param, const u32* __restrict__ gbase, u32* __restrict__ status, const SegList sl,
@@ -206,7 +207,9 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
     // DBG instantiations (TG_SWEEP_DEBUG, timing experiments only, results are wrong): dbg bit0 = no look-back wait,
     // bit1 = no matching, bit2 = linear instead of scattered write-out, bit3 = no write-out
     typedef typename ItemT<WORDS>::type Item;
-    typedef SweepCfg<WORDS, THREADS, IPT> C;
+    // TMA = false: no landing buffer and no bulk copies; the items are loaded straight into registers (coalesced 8/16-byte
+    // loads) and several small CTAs per SM hide each other's load latency and barriers instead of the double buffer
+    typedef SweepCfg<WORDS, THREADS, IPT, TMA> C;
     constexpr int ITEMS = C::ITEMS, TILE = C::TILE, NWARPS = C::NWARPS;
     constexpr int LB = TG_LB;   // look-back batch: predecessors fetched concurrently
     constexpr bool PF = TG_PF != 0;      // request the first batch before the scatter
@@ -215,8 +218,8 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
     // plain pointer arithmetic on the shared array keeps the shared address space (LDS/STS, 32-bit addresses)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Item* const buf0 = reinterpret_cast<Item*>(smem_raw);
-    Item* const buf1 = reinterpret_cast<Item*>(smem_raw + C::BUF_BYTES);
-    u32* const whist = reinterpret_cast<u32*>(smem_raw + 2 * C::BUF_BYTES);      // [NWARPS][RADIX]
+    Item* const buf1 = reinterpret_cast<Item*>(smem_raw + (C::NBUF - 1) * C::BUF_BYTES);
+    u32* const whist = reinterpret_cast<u32*>(smem_raw + C::NBUF * C::BUF_BYTES);      // [NWARPS][RADIX]
     u32* const goff = whist + NWARPS * RADIX;                                    // [RADIX]
     u32* const warp_tot = goff + RADIX;                                          // [16]
     u64* const mbar = reinterpret_cast<u64*>(warp_tot + 16);                     // [2]
@@ -250,11 +253,11 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
     // by ordinary loads.
     auto tma_shift = [&](const TileInfo& ti) -> u32 { return WORDS == 1 ? (ti.start & 1u) : 0u; };
     auto tma_ok = [&](const TileInfo& ti) -> bool {
-        if (ti.len != (u32)TILE) return false;
+        if (!TMA || ti.len != (u32)TILE) return false;
         return tma_shift(ti) == 0 || (size_t)ti.start + TILE + 1 <= n;
     };
 
-    if (tid == 0) {
+    if (TMA && tid == 0) {
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
         mbar_fence_init();
@@ -262,7 +265,7 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
     __syncthreads();
 
     u32 j = blockIdx.x;
-    if (j < num_tiles) {
+    if (TMA && j < num_tiles) {
         const TileInfo t0 = tile_info(j);
         if (tid == 0 && tma_ok(t0)) {
             const u32 sh = tma_shift(t0), bytes = C::TILE_BYTES + 16 * sh;
@@ -273,7 +276,7 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
     u32 phase = 0;        // bit b: parity of the next completion of mbar[b]
 
     for (u32 it = 0; j < num_tiles; j += gridDim.x, ++it) {
-        const int cur = it & 1;
+        const int cur = TMA ? (it & 1) : 0;
         Item* const buf = cur ? buf1 : buf0;
         Item* const nbuf = cur ? buf0 : buf1;
         const TileInfo ti = tile_info(j);
@@ -284,7 +287,7 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
         const u32* const gb = SEG ? sl.segbase + (size_t)ti.seg * RADIX : gbase;
 
         // prefetch the CTA's next tile (TMA unit, async proxy) into the other buffer
-        if (tid == 0 && j + gridDim.x < num_tiles) {
+        if (TMA && tid == 0 && j + gridDim.x < num_tiles) {
             const TileInfo tn = tile_info(j + gridDim.x);
             if (tma_ok(tn)) {
                 const u32 sh = tma_shift(tn), bytes = C::TILE_BYTES + 16 * sh;
@@ -462,7 +465,8 @@ __global__ void copy_items_kernel(const typename ItemT<WORDS>::type* __restrict_
 // launch configurations (threads per CTA, 8-byte words per thread, CTAs per SM); TG_SWEEP_CFG overrides the default
 struct SweepVariant { int threads, wpt, minb; };
 constexpr SweepVariant kSweepVariants[] = { { 512, 16, 1 }, { 256, 16, 2 }, { 256, 16, 3 }, { 384, 16, 2 },
-                                            { 512, 8, 2 },  { 256, 8, 4 },  { 512, 8, 3 },  { 1024, 8, 1 } };
+                                            { 512, 8, 2 },  { 256, 8, 4 },  { 512, 8, 3 },  { 1024, 8, 1 },
+                                            { 256, 16, 3 }, { 256, 16, 4 }, { 512, 16, 2 } };      // 8..10: no TMA staging
 constexpr int kNumSweepVariants = sizeof(kSweepVariants) / sizeof(kSweepVariants[0]);
 inline int sweep_cfg() {
     static int cfg = -1;
@@ -486,13 +490,13 @@ inline int sweep_debug() {
     return f;
 }
 
-template <int WORDS, int THREADS, int WPT, int MINB, class DigitFn, bool SEG = false, bool DBG = false>
+template <int WORDS, int THREADS, int WPT, int MINB, class DigitFn, bool SEG = false, bool DBG = false, bool TMA = true>
 int launch_partition_v(tg_ctx* ctx, const void* in, void* out, u32 n, const DigitFn& fn, const u32* gbase, u32* status,
                        const SegList& sl = SegList{ nullptr, nullptr, 0 }) {
     typedef typename ItemT<WORDS>::type Item;
     constexpr int IPT = WPT / WORDS;
-    typedef SweepCfg<WORDS, THREADS, IPT> C;
-    auto kern = partition_kernel<WORDS, THREADS, IPT, MINB, DigitFn, SEG, DBG>;
+    typedef SweepCfg<WORDS, THREADS, IPT, TMA> C;
+    auto kern = partition_kernel<WORDS, THREADS, IPT, MINB, DigitFn, SEG, DBG, TMA>;
     int ctas_per_sm = 0;
     auto it = ctx->kernel_cfg.find((const void*)kern);
     if (it != ctx->kernel_cfg.end()) ctas_per_sm = it->second;
@@ -535,6 +539,9 @@ int launch_partition(tg_ctx* ctx, const void* in, void* out, u32 n, const DigitF
     case 5: return launch_partition_v<WORDS, 256, 8, 4, DigitFn>(ctx, in, out, n, fn, gbase, status);
     case 6: return launch_partition_v<WORDS, 512, 8, 3, DigitFn>(ctx, in, out, n, fn, gbase, status);
     case 7: return launch_partition_v<WORDS, 1024, 8, 1, DigitFn>(ctx, in, out, n, fn, gbase, status);
+    case 8: return launch_partition_v<WORDS, 256, 16, 3, DigitFn, false, false, false>(ctx, in, out, n, fn, gbase, status);
+    case 9: return launch_partition_v<WORDS, 256, 16, 4, DigitFn, false, false, false>(ctx, in, out, n, fn, gbase, status);
+    case 10: return launch_partition_v<WORDS, 512, 16, 2, DigitFn, false, false, false>(ctx, in, out, n, fn, gbase, status);
     default: return launch_partition_v<WORDS, 512, 16, 1, DigitFn>(ctx, in, out, n, fn, gbase, status);
     }
 }
@@ -557,6 +564,9 @@ int launch_partition_seg(tg_ctx* ctx, const void* in, void* out, u32 n, const Di
     case 5: return launch_partition_v<WORDS, 256, 8, 4, DigitFn, true>(ctx, in, out, n, fn, nullptr, status, sl);
     case 6: return launch_partition_v<WORDS, 512, 8, 3, DigitFn, true>(ctx, in, out, n, fn, nullptr, status, sl);
     case 7: return launch_partition_v<WORDS, 1024, 8, 1, DigitFn, true>(ctx, in, out, n, fn, nullptr, status, sl);
+    case 8: return launch_partition_v<WORDS, 256, 16, 3, DigitFn, true, false, false>(ctx, in, out, n, fn, nullptr, status, sl);
+    case 9: return launch_partition_v<WORDS, 256, 16, 4, DigitFn, true, false, false>(ctx, in, out, n, fn, nullptr, status, sl);
+    case 10: return launch_partition_v<WORDS, 512, 16, 2, DigitFn, true, false, false>(ctx, in, out, n, fn, nullptr, status, sl);
     default: return launch_partition_v<WORDS, 512, 16, 1, DigitFn, true>(ctx, in, out, n, fn, nullptr, status, sl);
     }
 }

@@ -390,9 +390,10 @@ constexpr u32 AGG_FLUSH_FILL = AGG_SLOTS * 3 / 4;  // the table is emitted early
 // (`partial`: its aggregates are merged afterwards).  The unit is streamed through the table in rounds of AGG_UNIT
 // records; if the table would get too full it is emitted as partial aggregates and cleared (FlushPartition,
 // reduce_probing_hash_table.hpp:372-377).
+template <int OP>
 __global__ void __launch_bounds__(AGG_THREADS, 3)
 agg_units_kernel(const ulonglong2* __restrict__ in, const uint2* __restrict__ units /* {first record, records | partial << 31} */,
-                 u32 nunits, int op, u64 ident, ulonglong2* __restrict__ out, u64* __restrict__ cursor,
+                 u32 nunits, u64 ident, ulonglong2* __restrict__ out, u64* __restrict__ cursor,
                  ulonglong2* __restrict__ dup_out, u64* __restrict__ dup_cursor, u64* __restrict__ zero_slot) {
     extern __shared__ __align__(16) unsigned char agg_smem[];
     u64* const keys = reinterpret_cast<u64*>(agg_smem);
@@ -400,6 +401,7 @@ agg_units_kernel(const ulonglong2* __restrict__ in, const uint2* __restrict__ un
     u32* const scratch = reinterpret_cast<u32*>(vals + AGG_SLOTS);      // 36 words, 8-byte aligned
     u32* const fill = scratch + 36;
     const u32 lane = lane_id();
+    constexpr int op = OP;             // compile-time: the reduce function's switch folds away
     constexpr int EI = AGG_SLOTS / AGG_THREADS;
     auto emit_table = [&](bool partial) {
         u64 ek[EI], ev[EI];
@@ -435,6 +437,7 @@ agg_units_kernel(const ulonglong2* __restrict__ in, const uint2* __restrict__ un
             }
             u64 key[AGG_RPT], val[AGG_RPT];
             bool valid[AGG_RPT];
+            u32 claims = 0;            // slots this thread claimed in this round (one shared atomic per warp at its end)
 #pragma unroll
             for (int r = 0; r < AGG_RPT; ++r) {
                 const u32 i = r * AGG_THREADS + threadIdx.x;
@@ -444,46 +447,59 @@ agg_units_kernel(const ulonglong2* __restrict__ in, const uint2* __restrict__ un
             }
 #pragma unroll
             for (int r = 0; r < AGG_RPT; ++r) {
-                // Records of a popular key sit next to each other here (their segment holds little else): when at least a
-                // quarter of the warp carries the key of lane 0 (or of lane 16), those lanes are reduced in registers and one
-                // lane touches the table — 32 lanes spinning on one shared-memory CAS loop is the slow case.
+                // Lanes of the warp that carry the same key are reduced in registers first and one lane touches the table:
+                // records of a popular key sit next to each other here (their segment holds little else), and several lanes
+                // spinning on one shared-memory CAS loop is the slow case.  Equal keys have equal home slots: group the lanes
+                // by the 12 slot bits (ballots), let the lowest lane of a group speak for the lanes that really have its key.
                 u64 v = val[r];
                 bool mine = valid[r];
+                const u32 home = (u32)(key_hash(key[r]) >> AGG_SHIFT_SLOT) & (AGG_SLOTS - 1);
+                u32 peers = __ballot_sync(0xffffffffu, mine);
+                if (!mine) peers = 0;
 #pragma unroll
-                for (int cand = 0; cand < 32; cand += 16) {
-                    const u64 kc = __shfl_sync(0xffffffffu, key[r], cand);
-                    const bool member = mine && key[r] == kc;
-                    const u32 mask = __ballot_sync(0xffffffffu, member);
-                    if (__popc(mask) >= 8) {
-                        u64 tot = (op == TG_OP_FIRST) ? __shfl_sync(0xffffffffu, v, __ffs(mask) - 1)
-                                                      : warp_reduce_masked(op, v, member, ident);
-                        if (member) {
-                            mine = lane == (u32)(__ffs(mask) - 1);
-                            v = tot;
-                        }
-                    }
+                for (int bit = 0; bit < 12; ++bit) {
+                    const bool one = (home >> bit) & 1u;
+                    const u32 m = __ballot_sync(0xffffffffu, one);
+                    peers &= one ? m : ~m;
                 }
-                if (!mine) continue;
+                const int leader = mine ? __ffs(peers) - 1 : (int)lane;
+                const u64 kl = __shfl_sync(0xffffffffu, key[r], leader);
+                const bool follows = mine && key[r] == kl;                 // (a lane with another key in the same home slot: on its own)
+                const u32 samekey = __ballot_sync(0xffffffffu, follows);
+                const u32 group = follows ? (peers & samekey) : (mine ? (1u << lane) : 0u);
+                const bool leads = mine && ((group & ((1u << lane) - 1)) == 0);
+                u32 todo = __ballot_sync(0xffffffffu, leads && (group & (group - 1)) != 0);      // leaders of groups of >= 2 lanes
+                while (todo) {
+                    const int L = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const u32 gm = __shfl_sync(0xffffffffu, group, L);
+                    const bool member = (gm >> lane) & 1u;
+                    const u64 tot = (op == TG_OP_FIRST) ? __shfl_sync(0xffffffffu, v, L) : warp_reduce_masked(op, v, member, ident);
+                    if ((int)lane == L) v = tot;
+                }
+                if (!leads) continue;
                 if (key[r] == 0) {
                     // Key() == 0: reduced in a side slot, never probed (reduce_probing_hash_table.hpp:195-218)
                     u64 prev = atomicCAS(&zero_slot[0], 0ull, 1ull);
                     op_apply(op, &zero_slot[1], v, prev == 0);
                     continue;
                 }
-                u32 slot = (u32)(key_hash(key[r]) >> AGG_SHIFT_SLOT) & (AGG_SLOTS - 1);
+                u32 slot = home;
                 bool claimed = false;
                 while (true) {
                     u64 k = *(volatile u64*)&keys[slot];
                     if (k == 0) {
                         k = atomicCAS(&keys[slot], 0ull, key[r]);
                         claimed = k == 0;
-                        if (claimed) { atomicAdd(fill, 1u); break; }
+                        if (claimed) { ++claims; break; }
                     }
                     if (k == key[r]) break;
                     slot = (slot + 1) & (AGG_SLOTS - 1);
                 }
                 op_apply(op, &vals[slot], v, claimed);
             }
+            claims = __reduce_add_sync(0xffffffffu, claims);
+            if (lane == 0 && claims) atomicAdd(fill, claims);
             __syncthreads();
         }
         emit_table(partial);
@@ -571,12 +587,28 @@ int run_partitioned_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 n, void
     int agrid = ctx->sm_count * 3;
     if ((u32)agrid > nunits) agrid = (int)nunits;
     constexpr int AGG_SMEM = AGG_SLOTS * 16 + 36 * 4 + 32;
-    if (ctx->kernel_cfg.find((const void*)agg_units_kernel) == ctx->kernel_cfg.end()) {
-        TG_CUDA(ctx, cudaFuncSetAttribute(agg_units_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AGG_SMEM));
-        ctx->kernel_cfg[(const void*)agg_units_kernel] = 3;
+#define TG_AGG_LAUNCH(OPC)                                                                                              \
+    case OPC: {                                                                                                         \
+        auto kern = agg_units_kernel<OPC>;                                                                              \
+        if (ctx->kernel_cfg.find((const void*)kern) == ctx->kernel_cfg.end()) {                                         \
+            TG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AGG_SMEM));            \
+            ctx->kernel_cfg[(const void*)kern] = 3;                                                                     \
+        }                                                                                                               \
+        TG_LAUNCH_T(ctx, TG_K_AGGREGATE, kern, agrid, AGG_THREADS, AGG_SMEM, (const ulonglong2*)bufB, (const uint2*)d_units, \
+                    nunits, ident, (ulonglong2*)d_out, sc.cursor, d_dup, dup_cursor, sc.zero_slot);                     \
+        break;                                                                                                          \
     }
-    TG_LAUNCH_T(ctx, TG_K_AGGREGATE, agg_units_kernel, agrid, AGG_THREADS, AGG_SMEM, (const ulonglong2*)bufB, (const uint2*)d_units, nunits, op, ident,
-                (ulonglong2*)d_out, sc.cursor, d_dup, dup_cursor, sc.zero_slot);
+    switch (op) {
+        TG_AGG_LAUNCH(TG_OP_SUM_F64)
+        TG_AGG_LAUNCH(TG_OP_SUM_U64)
+        TG_AGG_LAUNCH(TG_OP_MIN_U64)
+        TG_AGG_LAUNCH(TG_OP_MAX_U64)
+        TG_AGG_LAUNCH(TG_OP_MIN_F64)
+        TG_AGG_LAUNCH(TG_OP_MAX_F64)
+        TG_AGG_LAUNCH(TG_OP_FIRST)
+    default: return tg_set_error(ctx, TG_ERR_ARG, "reduce: op %d", op);
+    }
+#undef TG_AGG_LAUNCH
     u64* h = (u64*)ctx->pinned + 2048;
     TG_CUDA(ctx, cudaMemcpyAsync(h, sc.cursor, 16, cudaMemcpyDeviceToHost, ctx->stream));
     TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
