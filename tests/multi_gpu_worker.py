@@ -117,6 +117,23 @@ def main():
         assert np.bitwise_xor.reduce(m[:, 1]) == np.bitwise_xor.reduce(m[:, 3])                                 # multiset xor
         assert all(m[r, 6] <= m[r + 1, 5] for r in range(world - 1))                                            # ranges ordered
     tg.free(d)
+
+    # ---- ReduceByKey above the threshold of the partitioned aggregation (pre phase, exchange, post phase): exact sums ----
+    nr, U = 3000000, 1 << 20
+    cdf = O.zipf_cdf(U)
+    d_cdf = tg.to_device(cdf)
+    d = tg.alloc(nr * 16)
+    tg.ck(tg.L.tg_gen_reduce_zipf(tg.h, d, rank * nr, nr, 42, d_cdf, U, 1))
+    rp, rc = C.c_void_p(), C.c_size_t()
+    tg.ck(tg.L.tg_reduce_by_key(tg.h, C.byref(capi.KVDesc(16, capi.OP_SUM_F64)), d, nr, C.byref(rp), C.byref(rc)))
+    red = tg.download(rp.value, rc.value * 16, O.KV)
+    assert np.all(O.hash_partition_ids(red["key"], world) == rank), "key on the wrong worker"
+    parts = gather(red, world)
+    if rank == 0:
+        cat = np.sort(np.concatenate(parts), order="key")
+        ref = O.reduce_simple(O.gen_reduce_zipf(0, nr * world, cdf, exact=1), O.OP_SUM_F64)
+        assert np.array_equal(cat, ref), "large ReduceByKey differs from the oracle"
+    tg.free(d); tg.free(d_cdf)
     dist.barrier()
     ctx.close()
     if rank == 0:

@@ -93,7 +93,7 @@ __device__ __forceinline__ u32 match_digit8(u32 d) {
 }
 
 // tile geometry of one launch configuration: THREADS threads, each owning IPT items of WORDS 8-byte words
-template <int WORDS, int THREADS, int IPT, bool TMA = true>
+template <int WORDS, int THREADS, int IPT, bool TMA = true, bool STORE = true>
 struct SweepCfg {
     static constexpr int ITEM_BYTES = 8 * WORDS;
     static constexpr int ITEMS = IPT;
@@ -103,7 +103,9 @@ struct SweepCfg {
     // 2 landing/exchange buffers | warp counters [NWARPS][RADIX] | goff [RADIX] | warp_tot [16] | mbar [2] | dig [TILE]
     static constexpr int BUF_BYTES = TILE_BYTES + 16;       // + one 16-byte granule: tiles that start at an odd 8-byte item
     static constexpr int NBUF = TMA ? 2 : 1;                // landing + exchange, or the exchange buffer alone
-    static constexpr int SMEM = NBUF * BUF_BYTES + NWARPS * RADIX * 4 + RADIX * 4 + 64 + 16 + TILE + 256;
+    // buffers | warp counters [NWARPS][RADIX] | goff [RADIX] | warp_tot [16] | mbar [2] | digit bytes [TILE] (only if the digit
+    // function's result is kept, kStoreDigit) | slack
+    static constexpr int SMEM = NBUF * BUF_BYTES + NWARPS * RADIX * 4 + RADIX * 4 + 64 + 16 + (STORE ? TILE : 0) + 128;
 };
 
 // per-bucket counts of one digit function (the pre-pass of a stand-alone partition)
@@ -209,7 +211,7 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
     typedef typename ItemT<WORDS>::type Item;
     // TMA = false: no landing buffer and no bulk copies; the items are loaded straight into registers (coalesced 8/16-byte
     // loads) and several small CTAs per SM hide each other's load latency and barriers instead of the double buffer
-    typedef SweepCfg<WORDS, THREADS, IPT, TMA> C;
+    typedef SweepCfg<WORDS, THREADS, IPT, TMA, DigitFn::kStoreDigit> C;
     constexpr int ITEMS = C::ITEMS, TILE = C::TILE, NWARPS = C::NWARPS;
     constexpr int LB = TG_LB;   // look-back batch: predecessors fetched concurrently
     constexpr bool PF = TG_PF != 0;      // request the first batch before the scatter
@@ -265,8 +267,9 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
     __syncthreads();
 
     u32 j = blockIdx.x;
+    TileInfo tnext = tile_info(j < num_tiles ? j : 0);        // descriptor of the tile of the next iteration, fetched one ahead
     if (TMA && j < num_tiles) {
-        const TileInfo t0 = tile_info(j);
+        const TileInfo t0 = tnext;
         if (tid == 0 && tma_ok(t0)) {
             const u32 sh = tma_shift(t0), bytes = C::TILE_BYTES + 16 * sh;
             mbar_expect_tx(&mbar[0], bytes);
@@ -279,7 +282,8 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
         const int cur = TMA ? (it & 1) : 0;
         Item* const buf = cur ? buf1 : buf0;
         Item* const nbuf = cur ? buf0 : buf1;
-        const TileInfo ti = tile_info(j);
+        const TileInfo ti = tnext;
+        if (j + gridDim.x < num_tiles) tnext = tile_info(j + gridDim.x);
         const u32 tile_base = ti.start;
         const bool full_tile = ti.len == (u32)TILE;
         const u32 tile_valid = ti.len;
@@ -288,7 +292,7 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
 
         // prefetch the CTA's next tile (TMA unit, async proxy) into the other buffer
         if (TMA && tid == 0 && j + gridDim.x < num_tiles) {
-            const TileInfo tn = tile_info(j + gridDim.x);
+            const TileInfo tn = tnext;
             if (tma_ok(tn)) {
                 const u32 sh = tma_shift(tn), bytes = C::TILE_BYTES + 16 * sh;
                 fence_proxy_async();
@@ -334,6 +338,7 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
         // ---- per-digit tile count; publish PARTIAL as early as possible; start the look-back loads
         u32 count = 0, my_start = 0;
         u32 lbv[PF ? LB : 1];
+        const u32 my_gb = tid < RADIX ? __ldg(&gb[tid]) : 0u;      // (requested early: needed after the look-back)
         u32* const my_status = status + (size_t)ti.row * RADIX + tid;       // predecessor k: my_status - k * RADIX
         if (tid < RADIX) {
 #pragma unroll
@@ -423,7 +428,7 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
                 if (!full_tile && tid == RADIX - 1) pub -= (u32)TILE - tile_valid;
                 st_relaxed_u32(my_status, (excl + pub) | FLAG_INCL);
             }
-            goff[tid] = gb[tid] + excl - my_start;
+            goff[tid] = my_gb + excl - my_start;
         }
         __syncthreads();
 
@@ -495,7 +500,7 @@ int launch_partition_v(tg_ctx* ctx, const void* in, void* out, u32 n, const Digi
                        const SegList& sl = SegList{ nullptr, nullptr, 0 }) {
     typedef typename ItemT<WORDS>::type Item;
     constexpr int IPT = WPT / WORDS;
-    typedef SweepCfg<WORDS, THREADS, IPT, TMA> C;
+    typedef SweepCfg<WORDS, THREADS, IPT, TMA, DigitFn::kStoreDigit> C;
     auto kern = partition_kernel<WORDS, THREADS, IPT, MINB, DigitFn, SEG, DBG, TMA>;
     int ctas_per_sm = 0;
     auto it = ctx->kernel_cfg.find((const void*)kern);

@@ -392,8 +392,8 @@ constexpr u32 AGG_FLUSH_FILL = AGG_SLOTS * 3 / 4;  // the table is emitted early
 // reduce_probing_hash_table.hpp:372-377).
 template <int OP>
 __global__ void __launch_bounds__(AGG_THREADS, 3)
-agg_units_kernel(const ulonglong2* __restrict__ in, const uint2* __restrict__ units /* {first record, records | partial << 31} */,
-                 u32 nunits, u64 ident, ulonglong2* __restrict__ out, u64* __restrict__ cursor,
+agg_units_kernel(const ulonglong2* __restrict__ in, const uint2* __restrict__ units /* {first record, records | dedup << 30 | partial << 31} */,
+                 u32* __restrict__ nunits_ptr, u64 ident, ulonglong2* __restrict__ out, u64* __restrict__ cursor,
                  ulonglong2* __restrict__ dup_out, u64* __restrict__ dup_cursor, u64* __restrict__ zero_slot) {
     extern __shared__ __align__(16) unsigned char agg_smem[];
     u64* const keys = reinterpret_cast<u64*>(agg_smem);
@@ -420,9 +420,16 @@ agg_units_kernel(const ulonglong2* __restrict__ in, const uint2* __restrict__ un
         if (threadIdx.x == 0) *fill = 0;
         __syncthreads();
     };
-    for (u32 unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+    const u32 nunits = nunits_ptr[0];
+    u32* const work = nunits_ptr + 1;           // dynamic scheduling: the long units are at the front of the list
+    while (true) {
+        if (threadIdx.x == 0) scratch[0] = atomicAdd(work, 1u);
+        __syncthreads();
+        const u32 unit = scratch[0];
+        __syncthreads();
+        if (unit >= nunits) break;
         const uint2 u = __ldg(&units[unit]);
-        const u32 start = u.x, len = u.y & 0x7fffffffu;
+        const u32 start = u.x, len = u.y & 0x3fffffffu;
         bool partial = (u.y >> 31) != 0;
         clear_table();
         for (u32 off = 0; off < len; off += AGG_UNIT) {
@@ -454,6 +461,11 @@ agg_units_kernel(const ulonglong2* __restrict__ in, const uint2* __restrict__ un
                 u64 v = val[r];
                 bool mine = valid[r];
                 const u32 home = (u32)(key_hash(key[r]) >> AGG_SHIFT_SLOT) & (AGG_SLOTS - 1);
+                // Lanes of the warp that carry the same key are reduced in registers first and one lane touches the table:
+                // records of a popular key sit next to each other here (their segment holds little else), and several lanes on
+                // one shared-memory CAS are replayed one after the other (measured: 5x the kernel time on Zipf keys).  Equal keys
+                // have equal home slots: group the lanes by the 12 slot bits (ballots); the lowest lane of a group speaks for
+                // the lanes that really have its key; all groups are reduced at once by pointer jumping along their lanes.
                 u32 peers = __ballot_sync(0xffffffffu, mine);
                 if (!mine) peers = 0;
 #pragma unroll
@@ -468,14 +480,16 @@ agg_units_kernel(const ulonglong2* __restrict__ in, const uint2* __restrict__ un
                 const u32 samekey = __ballot_sync(0xffffffffu, follows);
                 const u32 group = follows ? (peers & samekey) : (mine ? (1u << lane) : 0u);
                 const bool leads = mine && ((group & ((1u << lane) - 1)) == 0);
-                u32 todo = __ballot_sync(0xffffffffu, leads && (group & (group - 1)) != 0);      // leaders of groups of >= 2 lanes
-                while (todo) {
-                    const int L = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const u32 gm = __shfl_sync(0xffffffffu, group, L);
-                    const bool member = (gm >> lane) & 1u;
-                    const u64 tot = (op == TG_OP_FIRST) ? __shfl_sync(0xffffffffu, v, L) : warp_reduce_masked(op, v, member, ident);
-                    if ((int)lane == L) v = tot;
+                if (__any_sync(0xffffffffu, (group & (group - 1)) != 0)) {
+                    const u32 above = group & ~((2u << lane) - 1u);
+                    int nxt = above ? __ffs(above) - 1 : -1;
+#pragma unroll
+                    for (int step = 0; step < 5; ++step) {
+                        const int src = nxt < 0 ? (int)lane : nxt;
+                        const u64 other = __shfl_sync(0xffffffffu, v, src);
+                        const int nn = __shfl_sync(0xffffffffu, nxt, src);
+                        if (nxt >= 0) { v = op_combine(op, v, other); nxt = nn; }
+                    }
                 }
                 if (!leads) continue;
                 if (key[r] == 0) {
@@ -484,6 +498,7 @@ agg_units_kernel(const ulonglong2* __restrict__ in, const uint2* __restrict__ un
                     op_apply(op, &zero_slot[1], v, prev == 0);
                     continue;
                 }
+                // find (or claim) the key's slot: linear probing from the home slot (:229-248)
                 u32 slot = home;
                 bool claimed = false;
                 while (true) {
@@ -496,6 +511,8 @@ agg_units_kernel(const ulonglong2* __restrict__ in, const uint2* __restrict__ un
                     if (k == key[r]) break;
                     slot = (slot + 1) & (AGG_SLOTS - 1);
                 }
+                // (the compiler's shared-memory 64-bit atomics are the hardware-assisted ATOMS.CAST.SPIN form: a hand-written
+                // ld/atom.cas loop in PTX measured 2x slower for the whole kernel)
                 op_apply(op, &vals[slot], v, claimed);
             }
             claims = __reduce_add_sync(0xffffffffu, claims);
@@ -504,6 +521,58 @@ agg_units_kernel(const ulonglong2* __restrict__ in, const uint2* __restrict__ un
         }
         emit_table(partial);
         __syncthreads();
+    }
+}
+
+// Units straight from the segment table (the segments lie back to back in table order): 2^group_log2 consecutive segments
+// form a unit; a unit of more than AGG_UNIT records is streamed in rounds with the intra-warp reduction switched on
+// (dominated by popular keys), one of more than AGG_MAX_UNIT records is cut into partial pieces.  One CTA of 1024 threads.
+__global__ void __launch_bounds__(1024) build_units_kernel(const u32* __restrict__ segcount, int nseg, int group_log2,
+                                                            uint2* __restrict__ units, u32* __restrict__ nunits_out /* [0] = units, [1] = work counter */) {
+    __shared__ u32 wrec[32], wbig[32], wsml[32];
+    __shared__ u32 total_big;
+    const int ngroups = nseg >> group_log2, gsz = 1 << group_log2;
+    const int per = (ngroups + 1023) / 1024;
+    const int g0 = threadIdx.x * per, g1 = (g0 + per < ngroups) ? g0 + per : ngroups;
+    // long units (streamed in several rounds) go to the front of the list so that the dynamic scheduling starts them first
+    u32 rec = 0, big = 0, sml = 0;
+    for (int g = g0; g < g1; ++g) {
+        u32 len = 0;
+        for (int i = 0; i < gsz; ++i) len += segcount[(size_t)g * gsz + i];
+        rec += len;
+        if (len > (u32)AGG_UNIT) big += (len + AGG_MAX_UNIT - 1) / AGG_MAX_UNIT;
+        else if (len) sml += 1;
+    }
+    const u32 lane = lane_id(), warp = threadIdx.x >> 5;
+    u32 irec = rec, ibig = big, isml = sml;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 a = __shfl_up_sync(0xffffffffu, irec, o), b = __shfl_up_sync(0xffffffffu, ibig, o), c = __shfl_up_sync(0xffffffffu, isml, o);
+        if (lane >= (u32)o) { irec += a; ibig += b; isml += c; }
+    }
+    if (lane == 31) { wrec[warp] = irec; wbig[warp] = ibig; wsml[warp] = isml; }
+    __syncthreads();
+    u32 pos = irec - rec, bpos = ibig - big, spos = isml - sml;
+    for (u32 w = 0; w < warp; ++w) { pos += wrec[w]; bpos += wbig[w]; spos += wsml[w]; }
+    if (threadIdx.x == 1023) {
+        total_big = bpos + big;
+        nunits_out[0] = bpos + big + spos + sml;
+        nunits_out[1] = 0;
+    }
+    __syncthreads();
+    spos += total_big;
+    for (int g = g0; g < g1; ++g) {
+        u32 len = 0;
+        for (int i = 0; i < gsz; ++i) len += segcount[(size_t)g * gsz + i];
+        if (len == 0) continue;
+        if (len <= (u32)AGG_UNIT) units[spos++] = make_uint2(pos, len);
+        else if (len <= AGG_MAX_UNIT) units[bpos++] = make_uint2(pos, len | 0x40000000u);
+        else
+            for (u32 off = 0; off < len; off += AGG_MAX_UNIT) {
+                const u32 l = len - off < AGG_MAX_UNIT ? len - off : AGG_MAX_UNIT;
+                units[bpos++] = make_uint2(pos + off, l | 0xC0000000u);
+            }
+        pos += len;
     }
 }
 
@@ -544,48 +613,19 @@ int run_partitioned_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 n, void
     TG_TRY((launch_seg_count<2, HashLevelDigit>(ctx, bufA, sl, dl, segcount)));
     TG_LAUNCH(ctx, seg_scan_kernel, dim3(RADIX, 1), RADIX, 0, segcount, d_gbase1, 1, RADIX, segbase);
     TG_TRY((launch_partition_seg<2, HashLevelDigit>(ctx, bufA, bufB, (u32)n, dl.fn[0], status, sl)));
-    // (3) units: whole consecutive segments up to AGG_UNIT records; longer segments in pieces (partial)
-    u32* h_seg;
-    TG_TRY(tg_pinned_list(ctx, 0, table_words * 4 + (size_t)(n / AGG_UNIT + 3 * table_words + 16) * sizeof(uint2), (void**)&h_seg));
-    TG_CUDA(ctx, cudaMemcpyAsync(h_seg, segcount, table_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    // whole consecutive segments up to AGG_UNIT records share a unit; a longer segment is a unit of its own (streamed through
-    // the table in rounds), cut into partial pieces beyond AGG_MAX_UNIT records; long units first (static round robin)
-    uint2* h_units = (uint2*)(h_seg + table_words);
-    std::vector<uint2> small_units;
-    u32 nunits = 0, pos = 0, ustart = 0, ulen = 0;
-    for (size_t sgi = 0; sgi < table_words; ++sgi) {
-        const u32 c = h_seg[sgi];
-        if (c == 0) continue;
-        if (c > (u32)AGG_UNIT) {
-            if (ulen) { small_units.push_back(make_uint2(ustart, ulen)); ulen = 0; }
-            if (c <= AGG_MAX_UNIT) h_units[nunits++] = make_uint2(pos, c);
-            else
-                for (u32 off = 0; off < c; off += AGG_MAX_UNIT) {
-                    u32 l = c - off < AGG_MAX_UNIT ? c - off : AGG_MAX_UNIT;
-                    h_units[nunits++] = make_uint2(pos + off, l | 0x80000000u);
-                }
-        }
-        else {
-            if (ulen + c > (u32)AGG_UNIT) { small_units.push_back(make_uint2(ustart, ulen)); ulen = 0; }
-            if (ulen == 0) ustart = pos;
-            ulen += c;
-        }
-        pos += c;
-    }
-    if (ulen) small_units.push_back(make_uint2(ustart, ulen));
-    std::sort(h_units, h_units + nunits, [](const uint2& a, const uint2& b) { return (a.y & 0x7fffffffu) > (b.y & 0x7fffffffu); });
-    for (const uint2& su : small_units) h_units[nunits++] = su;
-    if (pos != (u32)n) return tg_set_error(ctx, TG_ERR_CUDA, "reduce: segment sizes add up to %u of %llu records", pos, (unsigned long long)n);
+    // (3) units of whole segments, built on the device from the segment table
+    int group_log2 = 0;
+    while (group_log2 < 16 && ((u64)n << (group_log2 + 1)) / (RADIX * RADIX) <= (u64)AGG_UNIT / 2) ++group_log2;
+    const size_t max_units = (table_words >> group_log2) + n / AGG_MAX_UNIT + 2;
     uint2* d_units;
-    TG_TRY(tg_ws_get(ctx, WS_SEG_TILES2, (size_t)nunits * sizeof(uint2) + 16, (void**)&d_units));
-    TG_CUDA(ctx, cudaMemcpyAsync(d_units, h_units, (size_t)nunits * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+    TG_TRY(tg_ws_get(ctx, WS_SEG_TILES2, max_units * sizeof(uint2) + 64, (void**)&d_units));
+    u32* d_nunits = (u32*)(d_units + max_units);
+    TG_LAUNCH(ctx, build_units_kernel, 1, 1024, 0, segcount, RADIX * RADIX, group_log2, d_units, d_nunits);
     ReduceScratch sc;
     TG_TRY(get_scratch(ctx, op, &sc));
     u64* dup_cursor = sc.cursor + 1;
     ulonglong2* d_dup = (ulonglong2*)bufA;                     // the first pass's output is dead: reuse it for the partial aggregates
-    int agrid = ctx->sm_count * 3;
-    if ((u32)agrid > nunits) agrid = (int)nunits;
+    const int agrid = ctx->sm_count * 3;
     constexpr int AGG_SMEM = AGG_SLOTS * 16 + 36 * 4 + 32;
 #define TG_AGG_LAUNCH(OPC)                                                                                              \
     case OPC: {                                                                                                         \
@@ -595,7 +635,7 @@ int run_partitioned_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 n, void
             ctx->kernel_cfg[(const void*)kern] = 3;                                                                     \
         }                                                                                                               \
         TG_LAUNCH_T(ctx, TG_K_AGGREGATE, kern, agrid, AGG_THREADS, AGG_SMEM, (const ulonglong2*)bufB, (const uint2*)d_units, \
-                    nunits, ident, (ulonglong2*)d_out, sc.cursor, d_dup, dup_cursor, sc.zero_slot);                     \
+                    d_nunits, ident, (ulonglong2*)d_out, sc.cursor, d_dup, dup_cursor, sc.zero_slot);                     \
         break;                                                                                                          \
     }
     switch (op) {
@@ -613,6 +653,7 @@ int run_partitioned_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 n, void
     TG_CUDA(ctx, cudaMemcpyAsync(h, sc.cursor, 16, cudaMemcpyDeviceToHost, ctx->stream));
     TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const u64 ndup = h[1];
+    if (getenv("TG_DEBUG_REDUCE")) fprintf(stderr, "[tg_reduce] n=%llu group_log2=%d emitted=%llu partial aggregates=%llu\n", (unsigned long long)n, group_log2, (unsigned long long)h[0], (unsigned long long)ndup);
     // (4) merge the pieces of the long segments (and emit the zero key) through the HBM table, appended to d_out
     u64 cap = ndup ? ndup + ndup / 2 + 64 : 0;
     ulonglong2* tab = nullptr;

@@ -271,7 +271,8 @@ int partition_chunked(tg_ctx* ctx, const void* in, void* out, size_t n, const Di
     TG_LAUNCH(ctx, chunk_scan_kernel, 1, 4 * RADIX, 0, chunkcount, g.nchunks, totals, gbase, chunkbase);
     std::vector<u32> chunk_size(g.nchunks, g.chunk_items);
     chunk_size[g.nchunks - 1] = (u32)(n - (size_t)(g.nchunks - 1) * g.chunk_items);
-    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));          // the pinned staging of an earlier list is free again
+    // (pinned staging buffer 0: every operator ends with a stream synchronisation and the uses of one staging buffer inside an
+    // operator are separated by one, so the list staged there before has been copied)
     uint4* d_tiles;
     u32 total = 0;
     TG_TRY(build_tile_list(ctx, g.nchunks, chunk_size.data(), tile_items<WORDS>(), 0, WS_SEG_TILES2, &d_tiles, &total));
