@@ -259,10 +259,13 @@ def main():
     value = n * world / (ms_per_step / 1e3)
     pass_launch_ms = part_ms / max(part_cnt, 1)
     achieved = SORT_PASS_BYTES_PER_KEY * n / (pass_launch_ms / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "tgp::partition_kernel<1,512,16,1,RadixDigit,SEG> (one stable 8-bit partition pass: "
+    roofline = {"bound": "hbm", "kernel": "tgp::partition_kernel<1,256,16,3,RadixDigit,SEG> (one stable 8-bit partition pass: "
                                           "read 8 B + write 8 B per key)",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "peak_source": peak_src, "traffic": None,
+                "peak_source": peak_src,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on 1e8 keys, from the committed
+                # `ncu --set full` capture profiles/r1e_segmented_pass.txt (834.7 MB + 782.6 MB); scaled to this run's n
+                "traffic": (834.701824e6 + 782.626560e6) * (n / 1e8), "traffic_source": "profiles/r1e_segmented_pass.txt (ncu, n=1e8)",
                 "algorithmic_bytes_per_launch": SORT_PASS_BYTES_PER_KEY * n, "launch_ms": pass_launch_ms,
                 "launches_timed": part_cnt,
                 "step_share": {"partition_ms": part_ms / K, "partition_launches_per_step": part_cnt / K,
@@ -329,7 +332,7 @@ def main():
         extra = {"reduce_records_per_s": rn * world / (r_step / 1e3), "reduce_ms_per_step": r_step,
                  "reduce_distinct_out": int(sum_over_ranks(float(rcount.value), world)),
                  "reduce_config": {"workload": "reduce_pair_u64_f64_zipf_s1_U2^26", "records_per_gpu": rn},
-                 "reduce_roofline": {"bound": "hbm", "kernel": "tgp::partition_kernel<2,512,8,1,HashLevelDigit,SEG> (one hash-digit pass)",
+                 "reduce_roofline": {"bound": "hbm", "kernel": "tgp::partition_kernel<2,256,8,3,HashLevelDigit,SEG> (one hash-digit pass)",
                                      "achieved": r_ach, "peak": hbm_peak, "unit": "GB/s",
                                      "frac": (r_ach / hbm_peak) if r_ach else None, "launch_ms": part_launch,
                                      "step_share": {"partition_ms": rpart_ms / 3, "partition_launches_per_step": rpart_cnt / 3,

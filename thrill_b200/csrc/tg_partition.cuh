@@ -477,8 +477,8 @@ inline int sweep_cfg() {
     static int cfg = -1;
     if (cfg < 0) {
         const char* e = getenv("TG_SWEEP_CFG");
-        cfg = e ? atoi(e) : 0;
-        if (cfg < 0 || cfg >= kNumSweepVariants) cfg = 0;
+        cfg = e ? atoi(e) : 2;          // measured best on B200 for 8- and 16-byte items (profiles/r1e_segmented_pass.txt)
+        if (cfg < 0 || cfg >= kNumSweepVariants) cfg = 2;
     }
     return cfg;
 }
