@@ -403,17 +403,43 @@ agg_units_kernel(const ulonglong2* __restrict__ in, const uint2* __restrict__ un
     const u32 lane = lane_id();
     constexpr int op = OP;             // compile-time: the reduce function's switch folds away
     constexpr int EI = AGG_SLOTS / AGG_THREADS;
+    // The number of used slots is known (`fill`) before the table is read back: the output range is reserved first and the
+    // L2 round trip of that atomic overlaps the scan of the table.  All threads call it after a barrier that follows the
+    // last insert.
+    u64* const out_base = reinterpret_cast<u64*>(scratch + 38);      // 8-byte aligned (scratch + 36 is `fill`)
     auto emit_table = [&](bool partial) {
+        u64 base_reg = 0;
+        if (threadIdx.x == 0) {
+            const u32 cnt = *(volatile u32*)fill;
+            if (cnt) base_reg = atomicAdd(partial ? dup_cursor : cursor, (u64)cnt);     // consumed after the table scan below
+        }
         u64 ek[EI], ev[EI];
-        bool has[EI];
+        u32 mine = 0;
 #pragma unroll
         for (int j = 0; j < EI; ++j) {
             const u32 i = j * AGG_THREADS + threadIdx.x;
             ek[j] = keys[i]; ev[j] = vals[i];
-            has[j] = ek[j] != 0;
+            mine += ek[j] != 0 ? 1u : 0u;
         }
-        if (partial) emit_block<EI>(dup_out, dup_cursor, ek, ev, has, scratch);
-        else emit_block<EI>(out, cursor, ek, ev, has, scratch);
+        // exclusive scan of `mine` over the CTA
+        u32 incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (u32)o) incl += t;
+        }
+        const u32 warp = threadIdx.x >> 5;
+        if (lane == 31) scratch[warp] = incl;
+        if (threadIdx.x == 0) *out_base = base_reg;
+        __syncthreads();
+        u32 before = incl - mine;
+        for (u32 w = 0; w < warp; ++w) before += scratch[w];
+        ulonglong2* const dst = (partial ? dup_out : out) + *out_base + before;
+        u32 k = 0;
+#pragma unroll
+        for (int j = 0; j < EI; ++j)
+            if (ek[j] != 0) dst[k++] = make_ulonglong2(ek[j], ev[j]);
+        __syncthreads();                                             // scratch / out_base are reused
     };
     auto clear_table = [&]() {
         for (u32 i = threadIdx.x; i < AGG_SLOTS; i += AGG_THREADS) { keys[i] = 0; vals[i] = ident; }
@@ -431,33 +457,36 @@ agg_units_kernel(const ulonglong2* __restrict__ in, const uint2* __restrict__ un
         const uint2 u = __ldg(&units[unit]);
         const u32 start = u.x, len = u.y & 0x3fffffffu;
         bool partial = (u.y >> 31) != 0;
-        clear_table();
-        for (u32 off = 0; off < len; off += AGG_UNIT) {
-            // every thread reads the fill count of the finished rounds between two barriers: a uniform decision
-            const u32 filled = *(volatile u32*)fill;
-            __syncthreads();
-            const u32 rlen = len - off < (u32)AGG_UNIT ? len - off : (u32)AGG_UNIT;
-            if (off && filled + rlen > AGG_FLUSH_FILL) {       // this round could take the table beyond 3/4 full
-                emit_table(true);
-                partial = true;
-                clear_table();
-            }
-            u64 key[AGG_RPT], val[AGG_RPT];
-            bool valid[AGG_RPT];
-            u32 claims = 0;            // slots this thread claimed in this round (one shared atomic per warp at its end)
+        u64 key[AGG_RPT], val[AGG_RPT];
+        bool valid[AGG_RPT];
+        auto load_round = [&](u32 off) {
+            const u32 rl = len - off < (u32)AGG_UNIT ? len - off : (u32)AGG_UNIT;
 #pragma unroll
             for (int r = 0; r < AGG_RPT; ++r) {
                 const u32 i = r * AGG_THREADS + threadIdx.x;
-                valid[r] = i < rlen;
+                valid[r] = i < rl;
                 ulonglong2 kv = valid[r] ? in[(size_t)start + off + i] : make_ulonglong2(0, 0);
                 key[r] = kv.x; val[r] = kv.y;
             }
+        };
+        load_round(0);            // in flight while the table is cleared
+        clear_table();
+        for (u32 off = 0; off < len; off += AGG_UNIT) {
+            if (off) {
+                // every thread reads the fill count of the finished rounds between two barriers: a uniform decision
+                const u32 filled = *(volatile u32*)fill;
+                __syncthreads();
+                const u32 rlen = len - off < (u32)AGG_UNIT ? len - off : (u32)AGG_UNIT;
+                if (filled + rlen > AGG_FLUSH_FILL) {          // this round could take the table beyond 3/4 full
+                    emit_table(true);
+                    partial = true;
+                    clear_table();
+                }
+                load_round(off);
+            }
+            u32 claims = 0;            // slots this thread claimed in this round (one shared atomic per warp at its end)
 #pragma unroll
             for (int r = 0; r < AGG_RPT; ++r) {
-                // Lanes of the warp that carry the same key are reduced in registers first and one lane touches the table:
-                // records of a popular key sit next to each other here (their segment holds little else), and several lanes
-                // spinning on one shared-memory CAS loop is the slow case.  Equal keys have equal home slots: group the lanes
-                // by the 12 slot bits (ballots), let the lowest lane of a group speak for the lanes that really have its key.
                 u64 v = val[r];
                 bool mine = valid[r];
                 const u32 home = (u32)(key_hash(key[r]) >> AGG_SHIFT_SLOT) & (AGG_SLOTS - 1);
@@ -626,7 +655,7 @@ int run_partitioned_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 n, void
     u64* dup_cursor = sc.cursor + 1;
     ulonglong2* d_dup = (ulonglong2*)bufA;                     // the first pass's output is dead: reuse it for the partial aggregates
     const int agrid = ctx->sm_count * 3;
-    constexpr int AGG_SMEM = AGG_SLOTS * 16 + 36 * 4 + 32;
+    constexpr int AGG_SMEM = AGG_SLOTS * 16 + 36 * 4 + 64;
 #define TG_AGG_LAUNCH(OPC)                                                                                              \
     case OPC: {                                                                                                         \
         auto kern = agg_units_kernel<OPC>;                                                                              \
