@@ -22,6 +22,9 @@ namespace tgp {
 #ifndef TG_PF
 #define TG_PF 1
 #endif
+#ifndef TG_LB_SEG
+#define TG_LB_SEG 8      // (a dominant segment's tiles still run concurrently at the tail of the list: keep the batch deep)
+#endif
 
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
@@ -213,7 +216,9 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
     // loads) and several small CTAs per SM hide each other's load latency and barriers instead of the double buffer
     typedef SweepCfg<WORDS, THREADS, IPT, TMA, DigitFn::kStoreDigit> C;
     constexpr int ITEMS = C::ITEMS, TILE = C::TILE, NWARPS = C::NWARPS;
-    constexpr int LB = TG_LB;   // look-back batch: predecessors fetched concurrently
+    // look-back batch (predecessors fetched concurrently): inside a segment the predecessor finished a wave ago, one or two
+    // loads find its inclusive prefix; the plain chained scan over concurrently processed tiles needs a deep batch
+    constexpr int LB = SEG ? TG_LB_SEG : TG_LB;
     constexpr bool PF = TG_PF != 0;      // request the first batch before the scatter
     static_assert(THREADS >= RADIX, "one thread per digit in the scan phases");
 
