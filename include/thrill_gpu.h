@@ -199,6 +199,19 @@ int tg_sort(tg_ctx* ctx, const tg_key_desc* desc, void* d_in, size_t n_local, ui
 int tg_reduce_by_key(tg_ctx* ctx, const tg_kv_desc* desc, const void* d_in, size_t n_local,
                      void** out_dptr, size_t* out_n);
 
+/* DIA<pair<size_t, V>>::ReduceToIndex(key = .first, reduce function on .second, result_size, neutral_element)
+ * (api/reduce_to_index.hpp:60-237; the PageRank step, examples/page_rank/page_rank.hpp:125-135): pre phase = local
+ * aggregation, range partition k -> k * p / result_size (core/reduce_functional.hpp:83-149, common/math.hpp:83-120),
+ * NCCL Alltoallv, dense post phase (core/reduce_by_index_post_phase.hpp:43-330).  Rank r receives the contiguous index
+ * range [ceil(r*size/p), ceil((r+1)*size/p)) as a dense array of 16-byte items in *out_dptr: item i = (i, fold of the values
+ * whose index is i), or *neutral_item16 where no item has that index.  *out_begin = first index of the range.  An index
+ * >= result_size is TG_ERR_ARG (the reference asserts).  Collective. */
+int tg_reduce_to_index(tg_ctx* ctx, const tg_kv_desc* desc, const void* d_in, size_t n_local, uint64_t result_size,
+                       const void* neutral_item16, void** out_dptr, size_t* out_n, uint64_t* out_begin);
+/* ... with a host File as input; the dense result is fetched with tg_fetch_output */
+int tg_reduce_to_index_file(tg_ctx* ctx, const tg_kv_desc* desc, const tg_block* in_blocks, size_t n_in_blocks,
+                            uint64_t result_size, const void* neutral_item16, size_t* out_items, uint64_t* out_begin);
+
 /* The same two operators with HOST Files on both sides (the drop-in call: GpuSortNode::Execute /
  * GpuReduceNode::StopPreOp in thrill_b200/host/): gathers the input Blocks to the device, runs the
  * operator, reports the output size; tg_fetch_output then scatters the result into caller-allocated

@@ -23,6 +23,7 @@
 #include <thrill/api/generate.hpp>
 #include <thrill/api/read_binary.hpp>
 #include <thrill/api/reduce_by_key.hpp>
+#include <thrill/api/reduce_to_index.hpp>
 #include <thrill/api/size.hpp>
 #include <thrill/api/sort.hpp>
 #include <thrill/common/stats_timer.hpp>
@@ -236,6 +237,36 @@ int main(int argc, char** argv) {
                         }
                         report(it, timer.SecondsDouble());
                     }
+                }
+            }
+            else if (op == "reduce_to_index") {
+                // DIA<pair<u64 index, double>>::ReduceToIndex(.first, sum of .second, size = universe) — the PageRank step
+                // (examples/page_rank/page_rank.hpp:125-135); neutral element = PairF() = (0, 0.0)
+                using PairF = std::pair<uint64_t, double>;
+                const size_t result_size = static_cast<size_t>(std::stoull(arg("universe", "1024")));
+                auto input = api::Generate(ctx, n, [&](size_t i) {
+                                               return PairF(key_of(i) % result_size, val_of(i));
+                                           }).Cache();
+                input.Keep(iters + 1);
+                input.Size();
+                for (int it = 0; it < iters; ++it) {
+                    ctx.net.Barrier();
+                    common::StatsTimerStart timer;
+                    auto red = input.ReduceToIndex(
+                        [](const PairF& p) { return static_cast<size_t>(p.first); },
+                        [](const PairF& a, const PairF& b) { return PairF(a.first, a.second + b.second); },
+                        result_size);
+                    if (out.empty() || it + 1 < iters) {
+                        red.Size();
+                        ctx.net.Barrier();
+                        timer.Stop();
+                    }
+                    else {
+                        std::vector<PairF> all = red.Gather(0);
+                        timer.Stop();
+                        if (ctx.my_rank() == 0) write_file(out, all);
+                    }
+                    report(it, timer.SecondsDouble());
                 }
             }
             else if (op == "terasort") {

@@ -761,6 +761,25 @@ uint64_t to_reduce_simple(const to_kv* in, uint64_t n, int op, to_kv* out) {
     return o + 1;
 }
 
+/* ReduceToIndex (api/reduce_to_index.hpp:60-237): the result has `size` items; item i is the fold (in input order) of
+ * all items whose index (key) is i, or the neutral element where there is none — ReduceByIndexPostPhase fills its
+ * dense table with neutral_element_ and folds the arrivals into it (core/reduce_by_index_post_phase.hpp:141-222); worker w
+ * holds a contiguous index range and the ranges are ordered, so the concatenation over workers is the dense array.
+ * Returns the number of items with an index >= size (an error for the caller: the reference asserts). */
+uint64_t to_reduce_to_index(const to_kv* in, uint64_t n, uint64_t size, to_kv neutral, int op, to_kv* out) {
+    unsigned char* seen = (unsigned char*)calloc((size_t)(size ? size : 1), 1);
+    uint64_t bad = 0;
+    for (uint64_t i = 0; i < size; ++i) out[i] = neutral;
+    for (uint64_t i = 0; i < n; ++i) {
+        uint64_t k = in[i].key;
+        if (k >= size) { ++bad; continue; }
+        if (!seen[k]) { out[k] = in[i]; seen[k] = 1; }
+        else out[k].val = apply_op(op, out[k].val, in[i].val);
+    }
+    free(seen);
+    return bad;
+}
+
 /* ========================================================================== */
 /* data::File layout of fixed-size items as written by BlockWriter (data/block_writer.hpp:61-67 block_size_
  * = min(start_block_size, max), :405-420 AllocateBlock doubles while 2*bs < max; :183-203 item starts are

@@ -86,6 +86,8 @@ uint64_t to_reduce_operator(const to_kv* in, const uint64_t* local_counts, uint3
                             uint64_t mem_limit_bytes, int op, to_kv* out, uint64_t* out_counts);
 /* straightforward aggregate used as the scalable CPU checker: sort by key, fold equal keys in input order */
 uint64_t to_reduce_simple(const to_kv* in, uint64_t n, int op, to_kv* out);
+/* api/reduce_to_index.hpp:60-237, core/reduce_by_index_post_phase.hpp:141-222: dense result of `size` items */
+uint64_t to_reduce_to_index(const to_kv* in, uint64_t n, uint64_t size, to_kv neutral, int op, to_kv* out);
 
 /* ---- data::File / data::Block layout (data/file.hpp:56-283, data/block.hpp:52-145) ---- */
 typedef struct {

@@ -51,6 +51,13 @@ def main():
     # uniform keys, u64 sum
     O.run_ref_driver(workers=2, op="reduce_u64", gen="uniform", universe=3000, n=100000, out=out)
     g["reduce_u64_uniform_u3000_100000_w2"] = np.sort(np.fromfile(out, dtype=REDUCE_OUT), order="key")
+    # ReduceToIndex (the PageRank step): dense result, exact-mode doubles (bit-exact) and real doubles (tolerance)
+    for exact, w in ((1, 3), (0, 4)):
+        O.run_ref_driver(workers=w, op="reduce_to_index", gen="zipf", universe=1000, n=20000, exact=exact, out=out)
+        g["reduce_to_index_zipf_u1000_20000_exact%d_w%d" % (exact, w)] = np.fromfile(out, dtype=O.KV)
+    # sparse: most indices have no item and keep the neutral element (0, 0.0)
+    O.run_ref_driver(workers=5, op="reduce_to_index", gen="uniform", universe=50000, n=3000, exact=1, out=out)
+    g["reduce_to_index_uniform_u50000_3000_exact1_w5"] = np.fromfile(out, dtype=O.KV)
     # TeraSort records
     O.run_ref_driver(workers=3, op="terasort", n=20000, out=out)
     t = np.fromfile(out, dtype=np.uint8).reshape(-1, 100)

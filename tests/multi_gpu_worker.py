@@ -134,6 +134,17 @@ def main():
         ref = O.reduce_simple(O.gen_reduce_zipf(0, nr * world, cdf, exact=1), O.OP_SUM_F64)
         assert np.array_equal(cat, ref), "large ReduceByKey differs from the oracle"
     tg.free(d); tg.free(d_cdf)
+
+    # ---- ReduceToIndex (PageRank step): the concatenation over the workers is the dense array of the reference ----
+    cdf = O.zipf_cdf(1000)
+    dia = api.Generate(ctx, 20000, lambda idx: O.gen_reduce_zipf(int(idx[0]) if len(idx) else 0, len(idx), cdf, exact=1), dtype=None)
+    kv = dia.items.view(api.KV).copy()
+    kv["key"] %= 1000
+    red = api.DIA(ctx, kv).ReduceToIndex(api.KeyIsFirst, api.PlusDouble, 1000)
+    assert red.index_begin == (rank * 1000 + world - 1) // world
+    parts = gather(red.items, world)
+    if rank == 0:
+        assert np.array_equal(np.concatenate(parts), g["reduce_to_index_zipf_u1000_20000_exact1_w3"]), "ReduceToIndex differs from the reference"
     dist.barrier()
     ctx.close()
     if rank == 0:

@@ -22,6 +22,10 @@ KV = np.dtype([("key", "<u8"), ("val", "<u8")])
 BLOCK_META = np.dtype([("begin", "<u8"), ("end", "<u8"), ("first_item", "<u8"), ("num_items", "<u8")])
 
 
+class KVStruct(C.Structure):
+    _fields_ = [("key", C.c_uint64), ("val", C.c_uint64)]
+
+
 class KeyDesc(C.Structure):
     _fields_ = [("item_bytes", C.c_uint32), ("key_offset", C.c_uint32),
                 ("key_bytes", C.c_uint32), ("key_kind", C.c_uint32)]
@@ -60,6 +64,7 @@ def lib():
         L.to_reduce_operator.restype = u64
         L.to_reduce_operator.argtypes = [vp, vp, u32, u64, i32, vp, vp]
         L.to_reduce_simple.restype = u64; L.to_reduce_simple.argtypes = [vp, u64, i32, vp]
+        L.to_reduce_to_index.restype = u64; L.to_reduce_to_index.argtypes = [vp, u64, u64, KVStruct, i32, vp]
         L.to_file_layout.restype = u64; L.to_file_layout.argtypes = [u64, u32, u64, u64, vp, u64]
         L.to_gen_sort_uniform.argtypes = [vp, u64, u64, u64]
         L.to_gen_reduce_uniform.argtypes = [vp, u64, u64, u64, u64, i32]
@@ -248,6 +253,15 @@ def reduce_simple(kv, op):
     out = np.empty(max(len(kv), 1), dtype=KV)
     n = lib().to_reduce_simple(_p(kv), len(kv), op, _p(out))
     return out[:n]
+
+
+def reduce_to_index(kv, size, op, neutral=(0, 0)):
+    """dense ReduceToIndex result (api/reduce_to_index.hpp): `size` items, neutral where no item has that index"""
+    kv = np.ascontiguousarray(kv, dtype=KV)
+    out = np.empty(max(size, 1), dtype=KV)
+    bad = lib().to_reduce_to_index(_p(kv), len(kv), size, KVStruct(int(neutral[0]), int(neutral[1])), op, _p(out))
+    assert bad == 0, "%d indices out of range" % bad
+    return out[:size]
 
 
 # ---- layout ----------------------------------------------------------------

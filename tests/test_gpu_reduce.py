@@ -177,3 +177,54 @@ def test_partitioned_aggregate_all_distinct_and_f64_tolerance(ctx):
     assert np.array_equal(out["key"], ref["key"])
     a, b = out["val"].view(np.float64), ref["val"].view(np.float64)
     assert np.all(np.abs(a - b) <= F64_RTOL * np.maximum(1.0, np.abs(b)))
+
+
+# ---- ReduceToIndex (api/reduce_to_index.hpp:60-237, the PageRank step) ----------------------------------------------------
+
+def _reduce_to_index(ctx, kv, size, op, neutral=(0, 0)):
+    from thrill_b200 import capi
+    n = len(kv)
+    d_in = ctx.to_device(kv) if n else ctx.alloc(16)
+    neu = np.zeros(1, dtype=O.KV); neu["key"], neu["val"] = neutral
+    op_, on, ob = C.c_void_p(), C.c_size_t(), C.c_uint64()
+    ctx.ck(ctx.L.tg_reduce_to_index(ctx.h, C.byref(capi.KVDesc(16, op)), d_in, n, size, neu.ctypes.data,
+                                    C.byref(op_), C.byref(on), C.byref(ob)))
+    out = ctx.download(op_.value, on.value * 16, O.KV)
+    ctx.free(d_in)
+    return out, ob.value
+
+
+def test_reduce_to_index_golden_and_oracle(ctx):
+    """dense result vs the unmodified reference (golden) — exact-mode doubles bit-identical, missing indices neutral — and
+    vs the oracle for the other reduce functions, a non-zero neutral element and an input above the partitioned-aggregation
+    threshold"""
+    from thrill_b200 import capi
+    g = golden()
+    kv = O.gen_reduce_zipf(0, 20000, O.zipf_cdf(1000), exact=1); kv["key"] %= 1000
+    out, begin = _reduce_to_index(ctx, kv, 1000, capi.OP_SUM_F64)
+    assert begin == 0 and np.array_equal(out, g["reduce_to_index_zipf_u1000_20000_exact1_w3"])
+    kv = O.gen_reduce_uniform(0, 3000, universe=50000, exact=1); kv["key"] %= 50000
+    out, _ = _reduce_to_index(ctx, kv, 50000, capi.OP_SUM_F64)
+    assert np.array_equal(out, g["reduce_to_index_uniform_u50000_3000_exact1_w5"])
+    kv = O.gen_reduce_zipf(0, 20000, O.zipf_cdf(1000)); kv["key"] %= 1000
+    out, _ = _reduce_to_index(ctx, kv, 1000, capi.OP_SUM_F64)
+    ref = g["reduce_to_index_zipf_u1000_20000_exact0_w4"]
+    assert np.array_equal(out["key"], ref["key"])
+    a, b = out["val"].view(np.float64), ref["val"].view(np.float64)
+    assert np.all(np.abs(a - b) <= F64_RTOL * np.maximum(1.0, np.abs(b)))
+    rng = np.random.RandomState(8)
+    n, size = 900000, 300000
+    kv = np.zeros(n, dtype=O.KV)
+    kv["key"] = rng.randint(0, size, size=n) // 3 * 3            # two thirds of the indices stay neutral
+    kv["val"] = rng.randint(0, 1 << 30, size=n)
+    for op, oop in ((capi.OP_SUM_U64, O.OP_SUM_U64), (capi.OP_MAX_U64, O.OP_MAX_U64), (capi.OP_MIN_U64, O.OP_MIN_U64)):
+        out, _ = _reduce_to_index(ctx, kv, size, op, neutral=(7, 99))
+        assert np.array_equal(out, O.reduce_to_index(kv, size, oop, neutral=(7, 99)))
+
+
+def test_reduce_to_index_rejects_out_of_range_index(ctx):
+    from thrill_b200 import capi
+    kv = np.zeros(100, dtype=O.KV)
+    kv["key"] = np.arange(100); kv["key"][17] = 5000
+    with pytest.raises(capi.ThrillGpuError):
+        _reduce_to_index(ctx, kv, 1000, capi.OP_SUM_U64)

@@ -121,3 +121,31 @@ def test_live_reference_reduce_with_zero_key(workers):
     assert np.array_equal(out["key"][order], ref["key"])
     assert np.array_equal(out["val"][order], ref["val"])
     assert np.array_equal(owner[order], ref["worker"])
+
+
+def _rti_input(gen, n, universe, exact):
+    if gen == "zipf":
+        kv = O.gen_reduce_zipf(0, n, O.zipf_cdf(universe), exact=exact)
+    else:
+        kv = O.gen_reduce_uniform(0, n, universe=universe, exact=exact)
+    kv["key"] %= universe                      # what ref_driver's reduce_to_index op feeds ReduceToIndex
+    return kv
+
+
+def test_golden_reduce_to_index_dense_result():
+    """ReduceToIndex (api/reduce_to_index.hpp:60-237, the PageRank step): the concatenation over the reference's workers is
+    the dense array; exact-mode doubles are bit-identical, real doubles within the stated tolerance, missing indices keep
+    the neutral element (0, 0.0)."""
+    g = golden()
+    ref = g["reduce_to_index_zipf_u1000_20000_exact1_w3"]
+    out = O.reduce_to_index(_rti_input("zipf", 20000, 1000, 1), 1000, O.OP_SUM_F64)
+    assert np.array_equal(out, ref)
+    ref = g["reduce_to_index_zipf_u1000_20000_exact0_w4"]
+    out = O.reduce_to_index(_rti_input("zipf", 20000, 1000, 0), 1000, O.OP_SUM_F64)
+    assert np.array_equal(out["key"], ref["key"])
+    a, b = out["val"].view(np.float64), ref["val"].view(np.float64)
+    assert np.all(np.abs(a - b) <= 1e-9 * np.maximum(1.0, np.abs(b)))
+    ref = g["reduce_to_index_uniform_u50000_3000_exact1_w5"]
+    out = O.reduce_to_index(_rti_input("uniform", 3000, 50000, 1), 50000, O.OP_SUM_F64)
+    assert np.array_equal(out, ref)
+    assert np.count_nonzero((ref["key"] == 0) & (ref["val"] == 0)) > 40000        # mostly neutral

@@ -181,6 +181,28 @@ class DIA(object):
         tg.ck(tg.L.tg_reduce_file(tg.h, C.byref(desc), blocks, nb, C.byref(n_out)))
         return DIA(self.ctx, self._fetch(n_out.value, KV, 16, _pinned_out))
 
+    # ---- DIA<T>::ReduceToIndex (api/reduce_to_index.hpp:60-237) -------------------------------------------------------
+    def ReduceToIndex(self, key_extractor, reduce_function, size, neutral_element=(0, 0), _pinned_out=None):
+        """items: pair<uint64_t index, 8-byte value>; result: this worker's contiguous slice of the dense array of `size`
+        16-byte items ((i, reduced value), or the neutral element where no item has index i); .index_begin = first index"""
+        if key_extractor is not KeyIsFirst:
+            raise capi.ThrillGpuError("ReduceToIndex: only the pair.first key extractor is recognised by the GPU path")
+        if not isinstance(reduce_function, _Functor) or reduce_function.code is None:
+            raise capi.ThrillGpuError("ReduceToIndex: reduce function %r is not one the GPU path recognises" % (reduce_function,))
+        if not (self.items.ndim == 1 and self.items.dtype == KV):
+            raise capi.ThrillGpuError("ReduceToIndex: items must be pair<uint64_t, 8-byte value>")
+        desc = capi.KVDesc(16, reduce_function.code)
+        blocks, nb = self._blocks(self.items)
+        neutral = np.zeros(1, dtype=KV)
+        neutral["key"], neutral["val"] = int(neutral_element[0]), int(neutral_element[1])
+        n_out, begin = C.c_size_t(), C.c_uint64()
+        tg = self.ctx.tg
+        tg.ck(tg.L.tg_reduce_to_index_file(tg.h, C.byref(desc), blocks, nb, int(size), neutral.ctypes.data,
+                                           C.byref(n_out), C.byref(begin)))
+        out = DIA(self.ctx, self._fetch(n_out.value, KV, 16, _pinned_out))
+        out.index_begin = int(begin.value)
+        return out
+
     def ReduceByKey(self, key_extractor, reduce_function):
         if key_extractor is not KeyIsFirst:
             raise capi.ThrillGpuError("ReduceByKey: only the pair.first key extractor is recognised by the GPU path")

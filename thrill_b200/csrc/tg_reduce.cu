@@ -696,6 +696,34 @@ int run_partitioned_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 n, void
     return read_cursor(ctx, sc, out_distinct);
 }
 
+// ---- ReduceToIndex: range partition and the dense result ---------------------------------------------------------------
+// destination worker of index k: k * p / size (ReduceByIndex / Range::FindPartition, core/reduce_functional.hpp:112-125,
+// common/math.hpp:98-100); out-of-range indices are parked on the last worker and reported by the dense scatter
+struct RangeDigit {
+    u64 size;
+    u32 p;
+    static constexpr bool kStoreDigit = true;
+    __device__ __forceinline__ u32 operator()(const ulonglong2& v, u32) const {
+        return v.x < size ? (u32)(v.x * p / size) : p - 1;
+    }
+};
+
+__global__ void fill_dense_kernel(ulonglong2* __restrict__ out, u64 n, ulonglong2 neutral) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = neutral;
+}
+
+// every index occurs at most once in `in` (it has been aggregated): plain stores
+__global__ void scatter_dense_kernel(const ulonglong2* __restrict__ in, u64 m, u64 begin, u64 count, ulonglong2* __restrict__ out,
+                                     u32* __restrict__ bad) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+        const ulonglong2 kv = in[i];
+        if (kv.x < begin || kv.x - begin >= count) { *bad = 1; continue; }
+        out[kv.x - begin] = kv;
+    }
+}
+
 int check_kv(tg_ctx* ctx, const tg_kv_desc* d) {
     if (!ctx || !d || d->item_bytes != 16 || d->op > TG_OP_FIRST)
         return tg_set_error(ctx, TG_ERR_ARG, "reduce: only 16-byte (u64 key, 8-byte value) items and TG_OP_* are supported");
@@ -790,6 +818,102 @@ int tg_reduce_by_key(tg_ctx* ctx, const tg_kv_desc* desc, const void* d_in, size
     TG_TRY(run_partitioned_aggregate(ctx, op, d_post_in, m_post, d_out, &distinct));
     *out_dptr = d_out;
     *out_n = (size_t)distinct;
+    return TG_OK;
+}
+
+int tg_reduce_to_index(tg_ctx* ctx, const tg_kv_desc* desc, const void* d_in, size_t n_local, uint64_t result_size,
+                       const void* neutral_item16, void** out_dptr, size_t* out_n, uint64_t* out_begin) {
+    TG_TRY(check_kv(ctx, desc));
+    if (!out_dptr || !out_n || !out_begin || !neutral_item16) return TG_ERR_ARG;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int op = (int)desc->op;
+    const int p = ctx->nranks, me = ctx->rank;
+    // the index range of this worker: Range(0, size).Partition(me, p) (common/math.hpp:85-94)
+    const u64 begin = ((u64)me * result_size + p - 1) / p, end = ((u64)(me + 1) * result_size + p - 1) / p;
+    const u64 count = end - begin;
+    if (count >= (1ull << 31)) return tg_set_error(ctx, TG_ERR_TOO_LARGE, "reduce_to_index: %llu indices per worker", (unsigned long long)count);
+    // pre phase: local aggregation by index
+    void* d_pre;
+    TG_TRY(tg_ws_get(ctx, WS_OUT, (n_local + 2) * 16, &d_pre));
+    u64 m = 0;
+    TG_TRY(run_partitioned_aggregate(ctx, op, d_in, n_local, d_pre, &m));
+    const void* d_post = d_pre;
+    u64 m_post = m;
+    if (p > 1) {
+        if (m >= (1u << 30)) return tg_set_error(ctx, TG_ERR_TOO_LARGE, "reduce_to_index: %llu partial aggregates", (unsigned long long)m);
+        void* d_send;
+        TG_TRY(tg_ws_get(ctx, WS_XCHG_SEND, (m + 2) * 16, &d_send));
+        RangeDigit fn = { result_size, (u32)p };
+        u32* d_counts = nullptr;
+        TG_TRY((partition_chunked<2, RangeDigit>(ctx, d_pre, d_send, m, fn, &d_counts, nullptr)));
+        u32* hc = (u32*)ctx->pinned;
+        TG_CUDA(ctx, cudaMemcpyAsync(hc, d_counts, RADIX * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        std::vector<u64> send_cnt(p), send_off(p + 1, 0);
+        for (int r = 0; r < p; ++r) { send_cnt[r] = hc[r]; send_off[r + 1] = send_off[r] + send_cnt[r]; }
+        u64* h = (u64*)ctx->pinned;
+        u64* d_ctl;
+        TG_TRY(tg_ws_get(ctx, WS_MISC, 1 << 16, (void**)&d_ctl));
+        for (int r = 0; r < p; ++r) h[r] = send_cnt[r];
+        TG_CUDA(ctx, cudaMemcpyAsync(d_ctl, h, 8 * p, cudaMemcpyHostToDevice, ctx->stream));
+        TG_NCCL(ctx, ncclAllGather(d_ctl, d_ctl + 64, p, ncclUint64, ctx->comm, ctx->stream));
+        TG_CUDA(ctx, cudaMemcpyAsync(h, d_ctl + 64, 8 * p * p, cudaMemcpyDeviceToHost, ctx->stream));
+        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        std::vector<u64> recv_cnt(p), recv_off(p + 1, 0);
+        for (int r = 0; r < p; ++r) { recv_cnt[r] = h[(size_t)r * p + me]; recv_off[r + 1] = recv_off[r] + recv_cnt[r]; }
+        ulonglong2* d_recv;
+        TG_TRY(tg_ws_get(ctx, WS_XCHG_RECV, (recv_off[p] + 2) * 16, (void**)&d_recv));
+        TG_NCCL(ctx, ncclGroupStart());
+        for (int r = 0; r < p; ++r) {
+            if (send_cnt[r]) TG_NCCL(ctx, ncclSend((const ulonglong2*)d_send + send_off[r], send_cnt[r] * 16, ncclUint8, r, ctx->comm, ctx->stream));
+            if (recv_cnt[r]) TG_NCCL(ctx, ncclRecv(d_recv + recv_off[r], recv_cnt[r] * 16, ncclUint8, r, ctx->comm, ctx->stream));
+        }
+        TG_NCCL(ctx, ncclGroupEnd());
+        // post phase, first half: one item per index
+        void* d_agg;
+        TG_TRY(tg_ws_get(ctx, WS_OUT, (recv_off[p] + 2) * 16, &d_agg));
+        u64 distinct = 0;
+        TG_TRY(run_partitioned_aggregate(ctx, op, d_recv, recv_off[p], d_agg, &distinct));
+        d_post = d_agg;
+        m_post = distinct;
+    }
+    // post phase, second half: the dense table filled with the neutral element (reduce_by_index_post_phase.hpp:141-160)
+    ulonglong2* d_dense;
+    TG_TRY(tg_ws_get(ctx, WS_DENSE, (count + 2) * 16, (void**)&d_dense));
+    ulonglong2 neutral;
+    memcpy(&neutral, neutral_item16, 16);
+    u32* d_bad;
+    TG_TRY(tg_ws_get(ctx, WS_MISC, 1 << 16, (void**)&d_bad));
+    d_bad += 12288;       // (48 KB into the scratch: behind the cursors of get_scratch at 32 KB)
+    TG_CUDA(ctx, cudaMemsetAsync(d_bad, 0, 4, ctx->stream));
+    if (count) TG_LAUNCH(ctx, fill_dense_kernel, ctx->sm_count * 8, 256, 0, d_dense, count, neutral);
+    if (m_post) TG_LAUNCH(ctx, scatter_dense_kernel, ctx->sm_count * 8, 256, 0, (const ulonglong2*)d_post, m_post, begin, count, d_dense, d_bad);
+    u32* hb = (u32*)ctx->pinned;
+    TG_CUDA(ctx, cudaMemcpyAsync(hb, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*hb) return tg_set_error(ctx, TG_ERR_ARG, "reduce_to_index: an index is not below result_size=%llu", (unsigned long long)result_size);
+    *out_dptr = d_dense;
+    *out_n = (size_t)count;
+    *out_begin = begin;
+    return TG_OK;
+}
+
+int tg_reduce_to_index_file(tg_ctx* ctx, const tg_kv_desc* desc, const tg_block* in_blocks, size_t n_in_blocks,
+                            uint64_t result_size, const void* neutral_item16, size_t* out_items, uint64_t* out_begin) {
+    TG_TRY(check_kv(ctx, desc));
+    if (!out_items || !out_begin) return TG_ERR_ARG;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t bytes = 0;
+    for (size_t i = 0; i < n_in_blocks; ++i) bytes += in_blocks[i].bytes;
+    if (bytes % 16) return tg_set_error(ctx, TG_ERR_ARG, "reduce_to_index_file: %zu bytes is not a multiple of 16", bytes);
+    void* d_in;
+    TG_TRY(tg_ws_get(ctx, WS_IN, bytes + 16, &d_in));
+    TG_TRY(tg_upload_blocks(ctx, d_in, in_blocks, n_in_blocks, nullptr));
+    void* out = nullptr;
+    size_t n_out = 0;
+    TG_TRY(tg_reduce_to_index(ctx, desc, d_in, bytes / 16, result_size, neutral_item16, &out, &n_out, out_begin));
+    ctx->out_ptr = out; ctx->out_items = n_out; ctx->out_item_bytes = 16;
+    *out_items = n_out;
     return TG_OK;
 }
 
