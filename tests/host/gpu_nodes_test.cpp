@@ -13,6 +13,7 @@
 #include <thrill/api/cache.hpp>
 #include <thrill/api/generate.hpp>
 #include <thrill/api/reduce_by_key.hpp>
+#include <thrill/api/reduce_to_index.hpp>
 #include <thrill/api/size.hpp>
 #include <thrill/api/sort.hpp>
 #include <thrill/common/stats_timer.hpp>
@@ -77,6 +78,22 @@ int main(int argc, char** argv) {
                 bool ok = cpu == gpu;
                 if (ctx.my_rank() == 0)
                     printf("%s ReducePair n=%zu distinct=%zu workers=%zu\n", ok ? "PASS" : "FAIL", n, cpu.size(), ctx.num_workers());
+                if (!ok) g_failures++;
+            }
+            // ---- ReduceToIndex (the PageRank step): dense result, missing indices keep the neutral element ----
+            {
+                using Pair = std::pair<uint64_t, double>;
+                const size_t size = 30011;
+                auto input = api::Generate(ctx, n / 4, [size](size_t i) {
+                                               uint64_t r = splitmix64(i + 99);
+                                               return Pair(r % size / 3 * 3, static_cast<double>(splitmix64(i + 5) % 1024));
+                                           }).Cache().Keep(2);
+                std::vector<Pair> cpu = input.ReduceToIndex(
+                    [](const Pair& p) { return static_cast<size_t>(p.first); },
+                    [](const Pair& a, const Pair& b) { return Pair(a.first, a.second + b.second); }, size).AllGather();
+                std::vector<Pair> gpu = thrill_gpu::ReduceToIndex(input, std::plus<double>(), size).AllGather();
+                bool ok = cpu == gpu && cpu.size() == size;
+                if (ctx.my_rank() == 0) printf("%s ReduceToIndex n=%zu size=%zu workers=%zu\n", ok ? "PASS" : "FAIL", n / 4, size, ctx.num_workers());
                 if (!ok) g_failures++;
             }
             // ---- Sort feeding ReducePair (GPU node -> GPU node through PushFile / OnPreOpFile) ----

@@ -251,8 +251,16 @@ class GpuReduceNode final : public thrill::api::DOpNode<ValueType>
 public:
     template <typename ParentDIA>
     GpuReduceNode(const ParentDIA& parent, const tg_kv_desc& desc)
-        : Super(parent.ctx(), "GpuReducePair", { parent.id() }, { parent.node() }),
-          desc_(desc), parent_stack_empty_(ParentDIA::stack_empty) {
+        : GpuReduceNode(parent, desc, false, 0, ValueType()) { }
+
+    //! to_index: ReduceToIndexNode (api/reduce_to_index.hpp:60-237) — dense result of result_size items, neutral_element
+    //! where no item has that index; worker r holds the index range Range(0, size).Partition(r, p)
+    template <typename ParentDIA>
+    GpuReduceNode(const ParentDIA& parent, const tg_kv_desc& desc, bool to_index, size_t result_size,
+                  const ValueType& neutral_element)
+        : Super(parent.ctx(), to_index ? "GpuReduceToIndex" : "GpuReducePair", { parent.id() }, { parent.node() }),
+          desc_(desc), parent_stack_empty_(ParentDIA::stack_empty),
+          to_index_(to_index), result_size_(result_size), neutral_(neutral_element) {
         // ReduceNode inserts each item into the pre-phase table (api/reduce_by_key.hpp:126-133); the GPU pre
         // phase wants the whole shard, so items are collected in a File first
         auto pre_op_fn = [this](const ValueType& input) { input_writer_.Put(input); };
@@ -277,7 +285,14 @@ public:
         size_t out_items = 0;
         {
             PinnedFileView view(input_file_, context_.local_worker_id());
-            Check(c, tg_reduce_file(c, &desc_, view.data(), view.size(), &out_items), "tg_reduce_file");
+            if (to_index_) {
+                static_assert(sizeof(ValueType) == 16, "16-byte (index, value) items");
+                uint64_t begin = 0;
+                Check(c, tg_reduce_to_index_file(c, &desc_, view.data(), view.size(), result_size_, &neutral_, &out_items, &begin),
+                      "tg_reduce_to_index_file");
+            }
+            else
+                Check(c, tg_reduce_file(c, &desc_, view.data(), view.size(), &out_items), "tg_reduce_file");
         }
         input_file_.Clear();
         FetchIntoFile(c, context_, out_items, sizeof(ValueType), reduced_file_);
@@ -294,6 +309,9 @@ public:
 private:
     tg_kv_desc desc_;
     const bool parent_stack_empty_;
+    const bool to_index_ = false;
+    const size_t result_size_ = 0;
+    const ValueType neutral_ = ValueType();
     thrill::data::File input_file_ { context_.GetFile(this) };
     thrill::data::File::Writer input_writer_;
     thrill::data::File reduced_file_ { context_.GetFile(this) };
@@ -323,6 +341,22 @@ auto ReducePair(const DIA<std::pair<Key, Value>, Stack>& dia, const ReduceFuncti
     using ValueType = std::pair<Key, Value>;
     auto node = tlx::make_counting<GpuReduceNode<ValueType> >(
         dia, tg_kv_desc { 16, ReduceDesc<Value, ReduceFunction>::op });
+    return DIA<ValueType>(node);
+}
+
+//! DIA<pair<uint64_t index, V>>::ReduceToIndex(key = .first, reduce function on .second, size, neutral_element)
+//! (api/reduce_to_index.hpp:239-393 front doors; examples/page_rank/page_rank.hpp:125-135)
+template <typename Key, typename Value, typename Stack, typename ReduceFunction>
+auto ReduceToIndex(const DIA<std::pair<Key, Value>, Stack>& dia, const ReduceFunction& /* reduce_function */,
+                   size_t size, const std::pair<Key, Value>& neutral_element = std::pair<Key, Value>()) {
+    static_assert(std::is_same<Key, uint64_t>::value && sizeof(Value) == 8 &&
+                  ReduceDesc<Value, ReduceFunction>::supported,
+                  "thrill_gpu::ReduceToIndex: this (Key, Value, ReduceFunction) has no GPU descriptor; "
+                  "use the stock dia.ReduceToIndex(key_extractor, fn, size)");
+    assert(dia.IsValid());
+    using ValueType = std::pair<Key, Value>;
+    auto node = tlx::make_counting<GpuReduceNode<ValueType> >(
+        dia, tg_kv_desc { 16, ReduceDesc<Value, ReduceFunction>::op }, true, size, neutral_element);
     return DIA<ValueType>(node);
 }
 
