@@ -120,6 +120,43 @@ def test_distributed_reduce_host_logic_matches_reference(tmp_path):
     assert np.array_equal(out["key"], ref["key"]) and np.array_equal(out["val"], ref["val"])
 
 
+def _rti_worker(rank, world, port, out_dir):
+    """ReduceToIndex around its kernels: range partition k*p/size (common/math.hpp:98-100), the worker's index range
+    Range(0,size).Partition(r,p) (:85-94), exchange, dense post phase — per-rank compute by the oracle"""
+    _init(rank, world, port)
+    import oracle_lib as O
+    from thrill_b200 import api
+    n, size = 20000, 1000
+    lo, hi = api._local_range(n, world, rank)
+    kv = O.gen_reduce_zipf(lo, hi - lo, O.zipf_cdf(size), exact=1)
+    kv["key"] %= size
+    pre = O.reduce_simple(kv, O.OP_SUM_F64)                                  # pre phase: local aggregation
+    dest = (pre["key"] * np.uint64(world)) // np.uint64(size)
+    send = [np.ascontiguousarray(pre[dest == r]) for r in range(world)]
+    allsend = _all_gather(send, world)
+    got = np.concatenate([allsend[src][rank] for src in range(world)])
+    begin, end = (rank * size + world - 1) // world, ((rank + 1) * size + world - 1) // world
+    assert len(got) == 0 or (got["key"].min() >= begin and got["key"].max() < end)
+    got = got.copy(); got["key"] -= np.uint64(begin)
+    dense = O.reduce_to_index(got, end - begin, O.OP_SUM_F64)
+    present = ~((dense["key"] == 0) & (dense["val"] == 0))
+    dense["key"][present] += np.uint64(begin)
+    if begin == 0 and len(got) and got["key"].min() == 0:
+        pass                                                                  # index 0 keeps key 0
+    np.save(os.path.join(out_dir, "rti%d.npy" % rank), dense)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_distributed_reduce_to_index_host_logic_matches_reference(tmp_path, world):
+    sys.path.insert(0, HERE)
+    from golden_util import golden
+    mp.spawn(_rti_worker, args=(world, 29720 + world, str(tmp_path)), nprocs=world, join=True)
+    cat = np.concatenate([np.load(os.path.join(str(tmp_path), "rti%d.npy" % r)) for r in range(world)])
+    assert np.array_equal(cat, golden()["reduce_to_index_zipf_u1000_20000_exact1_w3"])
+
+
 def test_local_range_matches_thrill_generate_split():
     from thrill_b200 import api
     for n in [0, 1, 7, 100, 4096, 10**8]:
