@@ -111,31 +111,6 @@ struct SweepCfg {
     static constexpr int SMEM = NBUF * BUF_BYTES + NWARPS * RADIX * 4 + RADIX * 4 + 64 + 16 + (STORE ? TILE : 0) + 128;
 };
 
-// per-bucket counts of one digit function (the pre-pass of a stand-alone partition)
-template <int WORDS, class DigitFn>
-__global__ void __launch_bounds__(512) bucket_count_kernel(const typename ItemT<WORDS>::type* __restrict__ in, u32 n,
-                                                           DigitFn fn, u32* __restrict__ gcount) {
-    __shared__ u32 sh[RADIX];
-    for (int i = threadIdx.x; i < RADIX; i += blockDim.x) sh[i] = 0;
-    __syncthreads();
-    const u32 stride = gridDim.x * blockDim.x;
-    for (u32 base = blockIdx.x * blockDim.x; base < n; base += stride) {
-        u32 i = base + threadIdx.x;
-        bool valid = i < n;
-        u32 act = __ballot_sync(0xffffffffu, valid);
-        if (!valid) continue;
-        u32 d = fn(in[i], i);
-        u32 d0 = __shfl_sync(act, d, __ffs(act) - 1);
-        if (__all_sync(act, d == d0)) {
-            if (lane_id() == (u32)(__ffs(act) - 1)) atomicAdd(&sh[d], __popc(act));
-        }
-        else atomicAdd(&sh[d], 1u);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < RADIX; i += blockDim.x)
-        if (sh[i]) atomicAdd(&gcount[i], sh[i]);
-}
-
 // exclusive scan of npass digit histograms -> global bases; skip[p] = 1 if one bin holds everything
 static __global__ void scan_hist_kernel(const u32* __restrict__ ghist, u32* __restrict__ gbase, u32* __restrict__ skip,
                                  int npass, u32 n) {
@@ -579,28 +554,6 @@ int launch_partition_seg(tg_ctx* ctx, const void* in, void* out, u32 n, const Di
     case 10: return launch_partition_v<WORDS, 512, 16, 2, DigitFn, true, false, false>(ctx, in, out, n, fn, nullptr, status, sl);
     default: return launch_partition_v<WORDS, 512, 16, 1, DigitFn, true>(ctx, in, out, n, fn, nullptr, status, sl);
     }
-}
-
-// stand-alone stable partition of n items into <= RADIX buckets: count pre-pass, scan, partition.
-// d_counts_out (device, RADIX u32) receives the bucket counts.
-template <int WORDS, class DigitFn>
-int partition_items(tg_ctx* ctx, const void* in, void* out, u32 n, const DigitFn& fn, u32** d_counts_out) {
-    typedef typename ItemT<WORDS>::type Item;
-    u32 num_tiles = num_tiles_for<WORDS>(n);
-    u32* hist;
-    TG_TRY(tg_ws_get(ctx, WS_SORT_HIST, (size_t)2 * RADIX * 4, (void**)&hist));
-    u32* status;
-    TG_TRY(tg_ws_get(ctx, WS_SORT_STATUS, (size_t)num_tiles * RADIX * 4, (void**)&status));
-    TG_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)2 * RADIX * 4, ctx->stream));
-    TG_CUDA(ctx, cudaMemsetAsync(status, 0, (size_t)num_tiles * RADIX * 4, ctx->stream));
-    if (n) {
-        auto cnt = bucket_count_kernel<WORDS, DigitFn>;
-        TG_LAUNCH(ctx, cnt, ctx->sm_count * 2, 512, 0, (const Item*)in, n, fn, hist);
-        TG_LAUNCH(ctx, scan_hist_kernel, 1, RADIX, 0, hist, hist + RADIX, (u32*)nullptr, 1, n);
-        TG_TRY((launch_partition<WORDS, DigitFn>(ctx, in, out, n, fn, hist + RADIX, status)));
-    }
-    if (d_counts_out) *d_counts_out = hist;
-    return TG_OK;
 }
 
 }  // namespace tgp

@@ -7,12 +7,13 @@
 // (api/reduce_by_key.hpp:109-114), and ReduceByHashPostPhase (core/reduce_by_hash_post_phase.hpp:44-281).
 //
 // GPU formulation (same result set; output order is table order = unspecified in the reference too):
-//   pre phase   : per-CTA shared-memory probing tables absorb the head of the key distribution (the Zipf
-//                 hot keys never reach global atomics); tables are flushed as partial aggregates
-//   partition   : stable 256-way partition kernel with digit = Hash128to64(0,key) % p   (p > 1 only)
-//   exchange    : NCCL Alltoallv of the p contiguous groups                             (p > 1 only)
-//   post phase  : open-addressing table in HBM (16-byte slots, atomicCAS on the key, native atomics on the
-//                 value), sized from the number of partial aggregates, then compaction of the used slots
+//   pre phase   : local aggregation of the worker's records ("partitioned aggregation", below): two stable partition
+//                 passes by two bytes of the key hash, then shared-memory probing tables over runs of whole segments
+//   partition   : stable partition pass with digit = Hash128to64(0,key) % p              (p > 1 only)
+//   exchange    : NCCL Alltoallv of the p contiguous groups                              (p > 1 only)
+//   post phase  : the same aggregation over the received partial aggregates             (p > 1 only)
+// Inputs below 2^18 records, and the pieces of segments that had to be split, go through an open-addressing table in
+// HBM (16-byte slots, atomicCAS on the key, native atomics on the value) + compaction of the used slots.
 #include <algorithm>
 #include <vector>
 
@@ -65,19 +66,7 @@ __device__ __forceinline__ void op_apply(int op, u64* slot_val, u64 val, bool cl
 
 __device__ __forceinline__ u64 key_hash(u64 key) { return hash128to64_dev(0, key); }
 
-// ---- pre phase: per-CTA private tables ------------------------------------------------------------------------
-// 64-bit shared-memory atomics (u64/f64 add, min, max) are CAS spin loops on sm_100 (SASS ATOMS.CAST.SPIN.64),
-// which collapse under the contention of the Zipf head; global-memory 64-bit reductions are native
-// (RED.E.ADD.F64 at the L2).  So every CTA owns a PRIVATE open-addressing table in global memory, small enough
-// that all tables stay L2 resident (296 x 128 KB = 38 MB of the 126 MB L2): the hot keys are reduced with
-// native L2 atomics on CTA-private addresses (no cross-SM contention on a hot address), the table is frozen once
-// 3/4 full and misses are passed through as partial aggregates of their own; the table is emitted at the end
-// (FlushAll, reduce_probing_hash_table.hpp:484-488).
-constexpr int PRE_THREADS = 512;
-constexpr int PRE_CTAS_PER_SM = 2;
-constexpr u32 PRE_SLOTS = 8192;                  // 16-byte slots: 128 KB per CTA
-constexpr int PRE_MAXPROBE = 4;
-
+// ---- output reservation shared by the table kernels --------------------------------------------------------------
 // append items to the global output: ONE atomic on the global cursor per CTA per call (a cursor bumped per
 // warp is a single hot L2 address: ~4M serialized atomics per 1.25e8 records, measured 3-4 ms).  All threads of
 // the CTA must call it; NITEMS items per thread; `scratch` = 34 u32 of shared memory.
@@ -116,90 +105,6 @@ __device__ __forceinline__ void emit_block(ulonglong2* __restrict__ out, u64* cu
     for (int i = 0; i < NITEMS; ++i)
         if (has[i]) out[pos++] = make_ulonglong2(key[i], val[i]);
     __syncthreads();                                             // scratch is reused by the next call
-}
-
-__device__ __forceinline__ u64 ld_cg_u64(const u64* p) {
-    u64 v;
-    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-constexpr int PRE_ITEMS = 4;       // records per thread between two output reservations
-
-__global__ void __launch_bounds__(PRE_THREADS, PRE_CTAS_PER_SM)
-preagg_kernel(const ulonglong2* __restrict__ in, u64 n, int op, ulonglong2* __restrict__ tables /* [grid][PRE_SLOTS], pre-set to (0, identity) */,
-              ulonglong2* __restrict__ out, u64* __restrict__ cursor, u64* __restrict__ zero_slot /* [0]=flag, [1]=value */) {
-    __shared__ u32 fill;
-    __shared__ __align__(8) u32 scratch[36];
-    ulonglong2* tab = tables + (size_t)blockIdx.x * PRE_SLOTS;
-    if (threadIdx.x == 0) fill = 0;
-    __syncthreads();
-    constexpr u64 STEP = (u64)PRE_THREADS * PRE_ITEMS;
-    const u64 per_cta = (((n + gridDim.x - 1) / gridDim.x) + STEP - 1) / STEP * STEP;
-    const u64 lo = per_cta * blockIdx.x;
-    const u64 hi = lo + per_cta < n ? lo + per_cta : n;
-    for (u64 base = lo; base < hi; base += STEP) {
-        u64 key[PRE_ITEMS], val[PRE_ITEMS], first[PRE_ITEMS];
-        u32 slot0[PRE_ITEMS];
-        bool spill[PRE_ITEMS], valid[PRE_ITEMS];
-        const bool frozen = *(volatile u32*)&fill > PRE_SLOTS * 3 / 4;
-        // all first probes of the PRE_ITEMS records in flight together (independent L2 round trips)
-#pragma unroll
-        for (int j = 0; j < PRE_ITEMS; ++j) {
-            u64 i = base + (u64)j * PRE_THREADS + threadIdx.x;
-            valid[j] = i < hi;
-            ulonglong2 kv = valid[j] ? in[i] : make_ulonglong2(0, 0);
-            key[j] = kv.x; val[j] = kv.y;
-            slot0[j] = (u32)(key_hash(kv.x) >> 32) & (PRE_SLOTS - 1);
-        }
-#pragma unroll
-        for (int j = 0; j < PRE_ITEMS; ++j) first[j] = __ldcg(&tab[slot0[j]].x);
-#pragma unroll
-        for (int j = 0; j < PRE_ITEMS; ++j) {
-            spill[j] = false;
-            if (!valid[j]) continue;
-            if (key[j] == 0) {
-                // Key() == 0: reduced in a side slot, never probed (reduce_probing_hash_table.hpp:195-218)
-                u64 prev = atomicCAS(&zero_slot[0], 0ull, 1ull);
-                op_apply(op, &zero_slot[1], val[j], prev == 0);
-                continue;
-            }
-            u32 slot = slot0[j];
-            u64 k = first[j];
-            spill[j] = true;
-#pragma unroll 1
-            for (int pr = 0; pr < PRE_MAXPROBE; ++pr) {
-                if (pr) k = ld_cg_u64(&tab[slot].x);
-                if (k == 0) {
-                    if (frozen) break;
-                    k = atomicCAS(&tab[slot].x, 0ull, key[j]);
-                    if (k == 0) atomicAdd(&fill, 1u);
-                }
-                if (k == 0 || k == key[j]) {
-                    op_apply(op, &tab[slot].y, val[j], k == 0);
-                    spill[j] = false;
-                    break;
-                }
-                slot = (slot + 1) & (PRE_SLOTS - 1);
-            }
-        }
-        // table misses pass through unreduced (legal partial aggregates)
-        emit_block<PRE_ITEMS>(out, cursor, key, val, spill, scratch);
-    }
-    // FlushAll: every reduction of this CTA must have landed in the L2 before the table is read back
-    __threadfence();
-    __syncthreads();
-    constexpr int FL = PRE_SLOTS / PRE_THREADS;
-    u64 key[FL], val[FL];
-    bool has[FL];
-#pragma unroll
-    for (int j = 0; j < FL; ++j) {
-        u32 i = j * PRE_THREADS + threadIdx.x;
-        key[j] = ld_cg_u64(&tab[i].x);
-        val[j] = ld_cg_u64(&tab[i].y);
-        has[j] = key[j] != 0;
-    }
-    emit_block<FL>(out, cursor, key, val, has, scratch);
 }
 
 // ---- post phase: open addressing in HBM ------------------------------------------------------------------------
@@ -294,31 +199,6 @@ int read_cursor(tg_ctx* ctx, const ReduceScratch& sc, u64* out) {
     return TG_OK;
 }
 
-// pre phase: n records -> m partial aggregates in d_pre (capacity n + grid*PRE_SLOTS + 1)
-size_t preagg_out_capacity(tg_ctx* ctx, u64 n) { return (size_t)n + (size_t)ctx->sm_count * PRE_CTAS_PER_SM * PRE_SLOTS + 2; }
-
-int run_preagg(tg_ctx* ctx, int op, const void* d_in, u64 n, void* d_pre, u64* out_m) {
-    ReduceScratch sc;
-    TG_TRY(get_scratch(ctx, op, &sc));
-    if (n) {
-        u64 ctas = (n + PRE_THREADS * 8 - 1) / (PRE_THREADS * 8);
-        int max_grid = ctx->sm_count * PRE_CTAS_PER_SM;
-        int grid = ctas < (u64)max_grid ? (int)ctas : max_grid;
-        ulonglong2* tables;
-        TG_TRY(tg_ws_get(ctx, WS_AUX2, (size_t)max_grid * PRE_SLOTS * 16, (void**)&tables));
-        if (op_identity_is_zero(op)) TG_CUDA(ctx, cudaMemsetAsync(tables, 0, (size_t)grid * PRE_SLOTS * 16, ctx->stream));
-        else {
-            u64 ident = (op == TG_OP_MIN_U64) ? ~0ull : (op == TG_OP_MIN_F64) ? 0x7FF0000000000000ull : 0xFFF0000000000000ull;
-            TG_LAUNCH(ctx, table_init_kernel, ctx->sm_count * 4, 512, 0, tables, (u64)grid * PRE_SLOTS, ident);
-        }
-        TG_LAUNCH_T(ctx, TG_K_PREAGG, preagg_kernel, grid, PRE_THREADS, 0, (const ulonglong2*)d_in, n, op, tables,
-                    (ulonglong2*)d_pre, sc.cursor, sc.zero_slot);
-    }
-    // the zero key's partial aggregate travels as one more item
-    TG_LAUNCH(ctx, compact_kernel, 1, 32, 0, (const ulonglong2*)nullptr, (u64)0, (ulonglong2*)d_pre, sc.cursor, sc.zero_slot);
-    return read_cursor(ctx, sc, out_m);
-}
-
 // post phase: m (partial) items -> distinct keys in d_out (capacity m)
 int run_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 m, void* d_out, u64* out_distinct) {
     ReduceScratch sc;
@@ -372,15 +252,6 @@ __device__ __forceinline__ u64 op_combine(int op, u64 a, u64 b) {
     case TG_OP_MAX_F64: return __longlong_as_double((long long)a) < __longlong_as_double((long long)b) ? b : a;
     default: return a;          // TG_OP_FIRST
     }
-}
-
-// reduce `v` over the lanes of `mask` (every lane of the warp calls it; lanes outside contribute the identity);
-// returns the total in every lane
-__device__ __forceinline__ u64 warp_reduce_masked(int op, u64 v, bool member, u64 ident) {
-    u64 x = member ? v : ident;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x = op_combine(op, x, __shfl_xor_sync(0xffffffffu, x, o));
-    return x;
 }
 
 constexpr u32 AGG_MAX_UNIT = 1u << 16;             // longer segments are cut (their pieces are merged afterwards)
