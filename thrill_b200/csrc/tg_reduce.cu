@@ -263,85 +263,94 @@ constexpr u32 AGG_FLUSH_FILL = AGG_SLOTS * 3 / 4;  // the table is emitted early
 // reduce_probing_hash_table.hpp:372-377).
 template <int OP>
 __global__ void __launch_bounds__(AGG_THREADS, 3)
-agg_units_kernel(const ulonglong2* __restrict__ in, const uint2* __restrict__ units /* {first record, records | dedup << 30 | partial << 31} */,
+agg_units_kernel(const ulonglong2* __restrict__ in, const uint2* __restrict__ units /* {first record, records | long << 30 | partial << 31} */,
                  u32* __restrict__ nunits_ptr, u64 ident, ulonglong2* __restrict__ out, u64* __restrict__ cursor,
                  ulonglong2* __restrict__ dup_out, u64* __restrict__ dup_cursor, u64* __restrict__ zero_slot) {
     extern __shared__ __align__(16) unsigned char agg_smem[];
     u64* const keys = reinterpret_cast<u64*>(agg_smem);
     u64* const vals = keys + AGG_SLOTS;
-    u32* const scratch = reinterpret_cast<u32*>(vals + AGG_SLOTS);      // 36 words, 8-byte aligned
-    u32* const fill = scratch + 36;
-    const u32 lane = lane_id();
+    u32* const scratch = reinterpret_cast<u32*>(vals + AGG_SLOTS);      // [0..31] warp totals of the emit scan
+    u32* const fill = scratch + 32;                                      // used slots of the table
+    u64* const out_base = reinterpret_cast<u64*>(scratch + 34);          // reserved output position (8-byte aligned)
+    uint4* const next_unit = reinterpret_cast<uint4*>(scratch + 36);     // [2] {unit id, first record, records|flags, -}, double buffered
+    const u32 lane = lane_id(), warp = threadIdx.x >> 5;
     constexpr int op = OP;             // compile-time: the reduce function's switch folds away
     constexpr int EI = AGG_SLOTS / AGG_THREADS;
-    // The number of used slots is known (`fill`) before the table is read back: the output range is reserved first and the
-    // L2 round trip of that atomic overlaps the scan of the table.  All threads call it after a barrier that follows the
-    // last insert.
-    u64* const out_base = reinterpret_cast<u64*>(scratch + 38);      // 8-byte aligned (scratch + 36 is `fill`)
-    auto emit_table = [&](bool partial) {
+    const u32 nunits = nunits_ptr[0];
+    u32* const work = nunits_ptr + 1;           // dynamic scheduling: the long units are at the front of the list
+
+    // Thread 0 fetches the id and the descriptor of a unit into next_unit[b] in three steps spread over the work of the
+    // unit before it, so that neither L2 round trip (the work counter, the descriptor) is waited for: fetch_id at the start
+    // of an emit, fetch_desc before the rows of the following round, fetch_store before that round's barrier.  Readers read
+    // next_unit[b] after that barrier.
+    u32 pend_id = 0xffffffffu;
+    uint2 pend_desc = make_uint2(0, 0);
+    int pend_buf = -1;
+    auto fetch_id = [&](int b) { pend_id = atomicAdd(work, 1u); pend_buf = b; };
+    auto fetch_desc = [&]() { if (pend_buf >= 0) pend_desc = pend_id < nunits ? __ldg(&units[pend_id]) : make_uint2(0, 0); };
+    auto fetch_store = [&]() {
+        if (pend_buf >= 0) { next_unit[pend_buf] = make_uint4(pend_id, pend_desc.x, pend_desc.y, 0); pend_buf = -1; }
+    };
+    u64 key[AGG_RPT], val[AGG_RPT];
+    bool valid[AGG_RPT];
+    auto load_round = [&](u32 first, u32 rl) {
+#pragma unroll
+        for (int r = 0; r < AGG_RPT; ++r) {
+            const u32 i = r * AGG_THREADS + threadIdx.x;
+            valid[r] = i < rl;
+            ulonglong2 kv = valid[r] ? in[(size_t)first + i] : make_ulonglong2(0, 0);
+            key[r] = kv.x; val[r] = kv.y;
+        }
+    };
+    // Emit the table and clear it in the same sweep (FlushPartitionEmit, reduce_probing_hash_table.hpp:443-482).  The
+    // number of used slots is known (`fill`): the output range is reserved first and the L2 round trip of that atomic
+    // overlaps the sweep.  fetch >= 0: thread 0 also starts fetching the unit after the next one into next_unit[fetch].  All
+    // threads call it after a barrier that follows the last insert; it ends with a barrier.
+    auto emit_and_clear = [&](bool partial, int fetch) {
         u64 base_reg = 0;
         if (threadIdx.x == 0) {
             const u32 cnt = *(volatile u32*)fill;
-            if (cnt) base_reg = atomicAdd(partial ? dup_cursor : cursor, (u64)cnt);     // consumed after the table scan below
+            if (cnt) base_reg = atomicAdd(partial ? dup_cursor : cursor, (u64)cnt);
+            if (fetch >= 0) fetch_id(fetch);
         }
-        u64 ek[EI], ev[EI];
         u32 mine = 0;
 #pragma unroll
-        for (int j = 0; j < EI; ++j) {
-            const u32 i = j * AGG_THREADS + threadIdx.x;
-            ek[j] = keys[i]; ev[j] = vals[i];
-            mine += ek[j] != 0 ? 1u : 0u;
-        }
-        // exclusive scan of `mine` over the CTA
+        for (int j = 0; j < EI; ++j) mine += keys[j * AGG_THREADS + threadIdx.x] != 0 ? 1u : 0u;
         u32 incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             u32 t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= (u32)o) incl += t;
         }
-        const u32 warp = threadIdx.x >> 5;
         if (lane == 31) scratch[warp] = incl;
-        if (threadIdx.x == 0) *out_base = base_reg;
+        if (threadIdx.x == 0) { *out_base = base_reg; *fill = 0; }
         __syncthreads();
         u32 before = incl - mine;
         for (u32 w = 0; w < warp; ++w) before += scratch[w];
-        ulonglong2* const dst = (partial ? dup_out : out) + *out_base + before;
-        u32 k = 0;
+        ulonglong2* dst = (partial ? dup_out : out) + *out_base + before;
 #pragma unroll
-        for (int j = 0; j < EI; ++j)
-            if (ek[j] != 0) dst[k++] = make_ulonglong2(ek[j], ev[j]);
-        __syncthreads();                                             // scratch / out_base are reused
-    };
-    auto clear_table = [&]() {
-        for (u32 i = threadIdx.x; i < AGG_SLOTS; i += AGG_THREADS) { keys[i] = 0; vals[i] = ident; }
-        if (threadIdx.x == 0) *fill = 0;
-        __syncthreads();
-    };
-    const u32 nunits = nunits_ptr[0];
-    u32* const work = nunits_ptr + 1;           // dynamic scheduling: the long units are at the front of the list
-    while (true) {
-        if (threadIdx.x == 0) scratch[0] = atomicAdd(work, 1u);
-        __syncthreads();
-        const u32 unit = scratch[0];
-        __syncthreads();
-        if (unit >= nunits) break;
-        const uint2 u = __ldg(&units[unit]);
-        const u32 start = u.x, len = u.y & 0x3fffffffu;
-        bool partial = (u.y >> 31) != 0;
-        u64 key[AGG_RPT], val[AGG_RPT];
-        bool valid[AGG_RPT];
-        auto load_round = [&](u32 off) {
-            const u32 rl = len - off < (u32)AGG_UNIT ? len - off : (u32)AGG_UNIT;
-#pragma unroll
-            for (int r = 0; r < AGG_RPT; ++r) {
-                const u32 i = r * AGG_THREADS + threadIdx.x;
-                valid[r] = i < rl;
-                ulonglong2 kv = valid[r] ? in[(size_t)start + off + i] : make_ulonglong2(0, 0);
-                key[r] = kv.x; val[r] = kv.y;
+        for (int j = 0; j < EI; ++j) {
+            const u32 i = j * AGG_THREADS + threadIdx.x;
+            const u64 k = keys[i];
+            if (k != 0) {
+                *dst++ = make_ulonglong2(k, vals[i]);
+                keys[i] = 0;
+                vals[i] = ident;
             }
-        };
-        load_round(0);            // in flight while the table is cleared
-        clear_table();
+        }
+        __syncthreads();
+    };
+
+    for (u32 i = threadIdx.x; i < AGG_SLOTS; i += AGG_THREADS) { keys[i] = 0; vals[i] = ident; }
+    if (threadIdx.x == 0) { *fill = 0; fetch_id(0); fetch_desc(); fetch_store(); }
+    __syncthreads();
+    uint4 cur = next_unit[0];
+    if (threadIdx.x == 0) fetch_id(1);                         // (stored before, read after the first round's barrier)
+    if (cur.x < nunits) load_round(cur.y, (cur.z & 0x3fffffffu) < (u32)AGG_UNIT ? (cur.z & 0x3fffffffu) : (u32)AGG_UNIT);
+    int nb = 1;                                                 // buffer that holds the next unit
+    while (cur.x < nunits) {
+        const u32 start = cur.y, len = cur.z & 0x3fffffffu;
+        bool partial = (cur.z >> 31) != 0;
         for (u32 off = 0; off < len; off += AGG_UNIT) {
             if (off) {
                 // every thread reads the fill count of the finished rounds between two barriers: a uniform decision
@@ -349,13 +358,13 @@ agg_units_kernel(const ulonglong2* __restrict__ in, const uint2* __restrict__ un
                 __syncthreads();
                 const u32 rlen = len - off < (u32)AGG_UNIT ? len - off : (u32)AGG_UNIT;
                 if (filled + rlen > AGG_FLUSH_FILL) {          // this round could take the table beyond 3/4 full
-                    emit_table(true);
+                    emit_and_clear(true, -1);
                     partial = true;
-                    clear_table();
                 }
-                load_round(off);
+                load_round(start + off, rlen);
             }
             u32 claims = 0;            // slots this thread claimed in this round (one shared atomic per warp at its end)
+            if (threadIdx.x == 0) fetch_desc();
 #pragma unroll
             for (int r = 0; r < AGG_RPT; ++r) {
                 u64 v = val[r];
@@ -417,10 +426,17 @@ agg_units_kernel(const ulonglong2* __restrict__ in, const uint2* __restrict__ un
             }
             claims = __reduce_add_sync(0xffffffffu, claims);
             if (lane == 0 && claims) atomicAdd(fill, claims);
+            if (threadIdx.x == 0) fetch_store();
             __syncthreads();
         }
-        emit_table(partial);
-        __syncthreads();
+        // the next unit's descriptor was fetched a whole unit ago: its first records are requested now and arrive while this
+        // unit's table is emitted; thread 0 fetches the unit after that during the emit
+        const uint4 nxt_unit = next_unit[nb];
+        if (nxt_unit.x < nunits)
+            load_round(nxt_unit.y, (nxt_unit.z & 0x3fffffffu) < (u32)AGG_UNIT ? (nxt_unit.z & 0x3fffffffu) : (u32)AGG_UNIT);
+        emit_and_clear(partial, nb ^ 1);
+        cur = nxt_unit;
+        nb ^= 1;
     }
 }
 
@@ -526,7 +542,7 @@ int run_partitioned_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 n, void
     u64* dup_cursor = sc.cursor + 1;
     ulonglong2* d_dup = (ulonglong2*)bufA;                     // the first pass's output is dead: reuse it for the partial aggregates
     const int agrid = ctx->sm_count * 3;
-    constexpr int AGG_SMEM = AGG_SLOTS * 16 + 36 * 4 + 64;
+    constexpr int AGG_SMEM = AGG_SLOTS * 16 + 36 * 4 + 2 * 16 + 32;
 #define TG_AGG_LAUNCH(OPC)                                                                                              \
     case OPC: {                                                                                                         \
         auto kern = agg_units_kernel<OPC>;                                                                              \

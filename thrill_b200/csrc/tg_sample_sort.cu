@@ -236,11 +236,26 @@ bool classify_first() {
 
 // splitters[i-1] = samples[(size_t)(i * double(S)/double(p))] over the (key, index)-sorted samples
 // (api/sort.hpp:357-372)
+// (only the p-1 order statistics are needed, not the sorted sample: nth_element on nested ranges instead of a full sort —
+// p * 2657 samples of 24 bytes cost ~2 ms to sort on the host at p = 8, on the critical path of every multi-worker sort)
+static void multi_select(CanonIdx* a, size_t lo, size_t hi, const size_t* pos, int np) {
+    if (np <= 0 || hi - lo < 2) return;
+    const int m = np / 2;
+    std::nth_element(a + lo, a + pos[m], a + hi, canonidx_less);
+    multi_select(a, lo, pos[m], pos, m);
+    multi_select(a, pos[m] + 1, hi, pos + m + 1, np - m - 1);
+}
+
 void pick_splitters(std::vector<CanonIdx>& samples, uint32_t p, std::vector<CanonIdx>* spl) {
-    std::sort(samples.begin(), samples.end(), canonidx_less);
     spl->clear();
-    double splitting_size = (double)samples.size() / (double)p;
-    for (uint32_t i = 1; i < p; ++i) spl->push_back(samples[(size_t)((double)i * splitting_size)]);
+    if (samples.empty()) return;
+    const double splitting_size = (double)samples.size() / (double)p;
+    std::vector<size_t> want, uniq;
+    for (uint32_t i = 1; i < p; ++i) want.push_back((size_t)((double)i * splitting_size));
+    for (size_t q : want)
+        if (uniq.empty() || uniq.back() != q) uniq.push_back(q);
+    multi_select(samples.data(), 0, samples.size(), uniq.data(), (int)uniq.size());
+    for (size_t q : want) spl->push_back(samples[q]);
 }
 
 template <int WORDS>
