@@ -249,6 +249,7 @@ def main():
     merge_ms, merge_cnt = tg.profile_get(capi.K_MERGE)
     fix_ms, fix_cnt = tg.profile_get(capi.K_FIXUP)
     segc_ms, segc_cnt = tg.profile_get(capi.K_SEGCOUNT)
+    xchg_ms, xchg_cnt = tg.profile_get(capi.K_EXCHANGE)
     tg.profile_enable(False)
     # cheap parity properties on the last result (outside the timed region)
     ok_sorted = tg.is_sorted(desc, out_p.value, out_n.value)
@@ -270,7 +271,7 @@ def main():
                 "launches_timed": part_cnt,
                 "step_share": {"partition_ms": part_ms / K, "partition_launches_per_step": part_cnt / K,
                                "radix_hist_ms": hist_ms / K, "segment_count_ms": segc_ms / K, "finishing_pass_ms": fix_ms / K,
-                               "merge_ms": merge_ms / K, "step_ms": ms_per_step},
+                               "merge_ms": merge_ms / K, "nccl_alltoallv_ms": xchg_ms / K, "step_ms": ms_per_step},
                 "prefix_sort_fallbacks": int(L.tg_prefix_sort_fallbacks(tg.h))}
 
     # ------------------------------------------------------------------ Sort, end to end (host Files) ---
@@ -323,6 +324,7 @@ def main():
         rpart_ms, rpart_cnt = tg.profile_get(capi.K_PARTITION)
         rhist_ms, rhist_cnt = tg.profile_get(capi.K_RADIX_HIST)
         rsegc_ms, rsegc_cnt = tg.profile_get(capi.K_SEGCOUNT)
+        rx_ms, rx_cnt = tg.profile_get(capi.K_EXCHANGE)
         tg.profile_enable(False)
         r_step = sum(r_ms) / len(r_ms)
         # dominant kernel: the stable partition pass over 16-byte records (the first two launches of a step move all
@@ -337,7 +339,7 @@ def main():
                                      "frac": (r_ach / hbm_peak) if r_ach else None, "launch_ms": part_launch,
                                      "step_share": {"partition_ms": rpart_ms / 3, "partition_launches_per_step": rpart_cnt / 3,
                                                     "count_ms": (rhist_ms + rsegc_ms) / 3, "aggregate_ms": agg_ms / 3,
-                                                    "compact_ms": cmp_ms / 3, "step_ms": r_step}}}
+                                                    "compact_ms": cmp_ms / 3, "nccl_alltoallv_ms": rx_ms / 3, "step_ms": r_step}}}
         tg.free(d_rin); tg.free(d_cdf)
 
     clocks = sampler.stop()

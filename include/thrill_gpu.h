@@ -106,7 +106,8 @@ uint64_t tg_prefix_sort_fallbacks(const tg_ctx* ctx);
  * bench.py's live roofline measurement.  tg_profile_get synchronises and returns the summed duration
  * and the number of launches of `kernel_class` since tg_profile_enable(ctx, 1). */
 enum { TG_K_RADIX_HIST = 0, TG_K_PARTITION = 1, TG_K_MERGE = 2, TG_K_PREAGG = 3, TG_K_AGGREGATE = 4,
-       TG_K_COMPACT = 5, TG_K_OTHER = 6, TG_K_FIXUP = 7, TG_K_SEGCOUNT = 8, TG_K_NUM = 9 };
+       TG_K_COMPACT = 5, TG_K_OTHER = 6, TG_K_FIXUP = 7, TG_K_SEGCOUNT = 8,
+       TG_K_EXCHANGE = 9 /* the NCCL Alltoallv (not a kernel of ours: timed like one) */, TG_K_NUM = 10 };
 int tg_profile_enable(tg_ctx* ctx, int on);
 int tg_profile_get(tg_ctx* ctx, int kernel_class, float* out_total_ms, uint64_t* out_launches);
 /* page-locked host memory (what the BlockPool arenas should be for full PCIe bandwidth; the host shim

@@ -689,12 +689,14 @@ int tg_reduce_by_key(tg_ctx* ctx, const tg_kv_desc* desc, const void* d_in, size
         for (int r = 0; r < p; ++r) { recv_cnt[r] = h[(size_t)r * p + me]; recv_off[r + 1] = recv_off[r] + recv_cnt[r]; }
         ulonglong2* d_recv;
         TG_TRY(tg_ws_get(ctx, WS_XCHG_RECV, (recv_off[p] + 2) * 16, (void**)&d_recv));
+        const int xprof_ = ctx->profile ? tg_prof_begin(ctx, TG_K_EXCHANGE) : -1;
         TG_NCCL(ctx, ncclGroupStart());
         for (int r = 0; r < p; ++r) {
             if (send_cnt[r]) TG_NCCL(ctx, ncclSend((const ulonglong2*)d_send + send_off[r], send_cnt[r] * 16, ncclUint8, r, ctx->comm, ctx->stream));
             if (recv_cnt[r]) TG_NCCL(ctx, ncclRecv(d_recv + recv_off[r], recv_cnt[r] * 16, ncclUint8, r, ctx->comm, ctx->stream));
         }
         TG_NCCL(ctx, ncclGroupEnd());
+        if (xprof_ >= 0) tg_prof_end(ctx, xprof_);
         d_post_in = d_recv;
         m_post = recv_off[p];
     }
@@ -750,12 +752,14 @@ int tg_reduce_to_index(tg_ctx* ctx, const tg_kv_desc* desc, const void* d_in, si
         for (int r = 0; r < p; ++r) { recv_cnt[r] = h[(size_t)r * p + me]; recv_off[r + 1] = recv_off[r] + recv_cnt[r]; }
         ulonglong2* d_recv;
         TG_TRY(tg_ws_get(ctx, WS_XCHG_RECV, (recv_off[p] + 2) * 16, (void**)&d_recv));
+        const int xprof_ = ctx->profile ? tg_prof_begin(ctx, TG_K_EXCHANGE) : -1;
         TG_NCCL(ctx, ncclGroupStart());
         for (int r = 0; r < p; ++r) {
             if (send_cnt[r]) TG_NCCL(ctx, ncclSend((const ulonglong2*)d_send + send_off[r], send_cnt[r] * 16, ncclUint8, r, ctx->comm, ctx->stream));
             if (recv_cnt[r]) TG_NCCL(ctx, ncclRecv(d_recv + recv_off[r], recv_cnt[r] * 16, ncclUint8, r, ctx->comm, ctx->stream));
         }
         TG_NCCL(ctx, ncclGroupEnd());
+        if (xprof_ >= 0) tg_prof_end(ctx, xprof_);
         // post phase, first half: one item per index
         void* d_agg;
         TG_TRY(tg_ws_get(ctx, WS_OUT, (recv_off[p] + 2) * 16, &d_agg));

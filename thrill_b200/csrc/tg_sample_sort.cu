@@ -330,12 +330,14 @@ int sort_multi_impl(tg_ctx* ctx, const tg_key_desc* desc, const KeyView& kv, voi
         if (n_recv >= (1u << 30)) return tg_set_error(ctx, TG_ERR_TOO_LARGE, "sort: %llu items received", (unsigned long long)n_recv);
         Item* d_recv;
         TG_TRY(tg_ws_get(ctx, WS_XCHG_RECV, (n_recv + 2) * s, (void**)&d_recv));
+        const int xprof_ = ctx->profile ? tg_prof_begin(ctx, TG_K_EXCHANGE) : -1;
         TG_NCCL(ctx, ncclGroupStart());
         for (int r = 0; r < p; ++r) {
             if (send_cnt[r]) TG_NCCL(ctx, ncclSend((const Item*)d_part + send_off[r], send_cnt[r] * s, ncclUint8, r, ctx->comm, ctx->stream));
             if (recv_cnt[r]) TG_NCCL(ctx, ncclRecv(d_recv + recv_off[r], recv_cnt[r] * s, ncclUint8, r, ctx->comm, ctx->stream));
         }
         TG_NCCL(ctx, ncclGroupEnd());
+        if (xprof_ >= 0) tg_prof_end(ctx, xprof_);
         // ReceiveItems + SortAndWriteToFile (:665-742): the received items arrive grouped by source worker in worker order, each
         // group in input order: the stable local sort leaves equal keys in global input order
         void* d_tmp2;
@@ -384,12 +386,14 @@ int sort_multi_impl(tg_ctx* ctx, const tg_key_desc* desc, const KeyView& kv, voi
     const u64 n_recv = recv_off[p];
     Item* d_recv;
     TG_TRY(tg_ws_get(ctx, WS_XCHG_RECV, (n_recv + 1) * s, (void**)&d_recv));
-    TG_NCCL(ctx, ncclGroupStart());
+    const int xprof_ = ctx->profile ? tg_prof_begin(ctx, TG_K_EXCHANGE) : -1;
+        TG_NCCL(ctx, ncclGroupStart());
     for (int r = 0; r < p; ++r) {
         if (send_cnt[r]) TG_NCCL(ctx, ncclSend((const Item*)d_sorted + send_off[r], send_cnt[r] * s, ncclUint8, r, ctx->comm, ctx->stream));
         if (recv_cnt[r]) TG_NCCL(ctx, ncclRecv(d_recv + recv_off[r], recv_cnt[r] * s, ncclUint8, r, ctx->comm, ctx->stream));
     }
     TG_NCCL(ctx, ncclGroupEnd());
+        if (xprof_ >= 0) tg_prof_end(ctx, xprof_);
 
     // (7) merge the p received sorted runs (source order = worker order: stable)
     Item* d_out;
@@ -531,12 +535,14 @@ int sort_records_impl(tg_ctx* ctx, const tg_key_desc* desc, void* d_in, size_t n
     if (n_recv >= (1u << 30)) return tg_set_error(ctx, TG_ERR_TOO_LARGE, "sort: received %llu records", n_recv);
     unsigned char* d_recv;
     TG_TRY(tg_ws_get(ctx, WS_XCHG_RECV, (n_recv + 1) * (size_t)rb, (void**)&d_recv));
-    TG_NCCL(ctx, ncclGroupStart());
+    const int xprof_ = ctx->profile ? tg_prof_begin(ctx, TG_K_EXCHANGE) : -1;
+        TG_NCCL(ctx, ncclGroupStart());
     for (int r = 0; r < p; ++r) {
         if (send_cnt[r]) TG_NCCL(ctx, ncclSend(d_sorted + send_off[r] * rb, send_cnt[r] * rb, ncclUint8, r, ctx->comm, ctx->stream));
         if (recv_cnt[r]) TG_NCCL(ctx, ncclRecv(d_recv + recv_off[r] * rb, recv_cnt[r] * rb, ncclUint8, r, ctx->comm, ctx->stream));
     }
     TG_NCCL(ctx, ncclGroupEnd());
+        if (xprof_ >= 0) tg_prof_end(ctx, xprof_);
     // merge the received runs through their tuples, then gather
     ulonglong2* d_rtup;
     ulonglong2* d_mtup;
