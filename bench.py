@@ -114,7 +114,7 @@ def ref_driver_path():
 _REF_WORKERS = {}
 
 
-def reference_workers(op):
+def reference_workers(op, extra=()):
     """The reference's throughput is not monotone in its worker count (p^2 streams, one thread per worker):
     calibrate on a small sample and keep the best of a few counts up to all host threads."""
     if op in _REF_WORKERS:
@@ -124,7 +124,7 @@ def reference_workers(op):
     best, best_t = cands[0], None
     for c in cands:
         try:
-            t = _run_reference_once(op, 20000000, 2, c)[-1]
+            t = _run_reference_once(op, 20000000 if op == "sort_u64" else 5000000, 2, c, extra)[-1]
         except Exception:
             continue
         if best_t is None or t < best_t:
@@ -168,6 +168,19 @@ def cpu_baseline_sort(n_sample):
     t = run_oracle_port_sort(n_sample // 10)
     return {"value": (n_sample // 10) / t, "unit": "keys/s", "cores": 1, "kind": "port",
             "sample": "oracle/thrill_oracle.c to_sort_items on %d keys, 1 thread (%.3f s)" % (n_sample // 10, t)}
+
+
+def cpu_baseline_reduce(n_sample):
+    """the unmodified reference's ReducePair<uint64_t,double>(plus) on the same Zipf(1.0, 2^26) generator, bounded sample"""
+    if not os.path.exists(ref_driver_path()):
+        return None
+    extra = ("gen=zipf", "universe=%d" % ZIPF_UNIVERSE)
+    workers = reference_workers("reduce_f64", extra)
+    times = _run_reference_once("reduce_f64", n_sample, 3, workers, extra)
+    t = statistics.median(times[1:]) if len(times) > 1 else times[0]
+    return {"value": n_sample / t, "unit": "records/s", "cores": workers, "kind": "reference",
+            "sample": "thrill_ref_driver Generate(Zipf s=1 U=2^26).Cache -> ReducePair(plus<double>).Size() of %d records, "
+                      "THRILL_WORKERS_PER_HOST=%d, median of iterations 2-3 (%.3f s)" % (n_sample, workers, t)}
 
 
 def main_reference(args):
@@ -348,6 +361,8 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_sort(n)
+        if rn and extra:
+            extra["reduce_cpu_baseline"] = cpu_baseline_reduce(min(rn, 25000000))
 
     if rank == 0:
         line = {"metric": "sort_keys_per_s", "value": value, "unit": "keys/s", "n_gpus": world, "steps": K, "warmup": W,
