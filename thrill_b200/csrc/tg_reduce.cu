@@ -25,14 +25,6 @@ using namespace tgp;
 namespace {
 
 // ---- the reduce functions the host shim recognises -----------------------------------------------------------
-__device__ __forceinline__ u64 op_identity(int op) {
-    switch (op) {
-    case TG_OP_MIN_U64: return ~0ull;
-    case TG_OP_MIN_F64: return 0x7FF0000000000000ull;      // +inf
-    case TG_OP_MAX_F64: return 0xFFF0000000000000ull;      // -inf
-    default: return 0ull;                                  // sums, max_u64, first
-    }
-}
 __host__ inline bool op_identity_is_zero(int op) {
     return op == TG_OP_SUM_F64 || op == TG_OP_SUM_U64 || op == TG_OP_MAX_U64 || op == TG_OP_FIRST;
 }
@@ -168,7 +160,6 @@ struct HashDigit {
     u32 p;
     static constexpr bool kStoreDigit = true;
     __device__ __forceinline__ u32 operator()(const ulonglong2& v, u32) const { return (u32)(key_hash(v.x) % p); }
-    __device__ __forceinline__ u32 operator()(const u64& v, u32) const { return (u32)(key_hash(v) % p); }
 };
 
 struct ReduceScratch {
