@@ -149,3 +149,18 @@ def test_golden_reduce_to_index_dense_result():
     out = O.reduce_to_index(_rti_input("uniform", 3000, 50000, 1), 50000, O.OP_SUM_F64)
     assert np.array_equal(out, ref)
     assert np.count_nonzero((ref["key"] == 0) & (ref["val"] == 0)) > 40000        # mostly neutral
+
+
+@needs_ref
+@pytest.mark.ref
+@pytest.mark.parametrize("workers,n,universe", [(1, 5000, 300), (2, 40000, 7001), (5, 3000, 100000)])
+def test_live_reference_reduce_to_index(workers, n, universe):
+    """live run of the unmodified reference's ReduceToIndex on a fresh shape (dense, sparse, more workers than data per
+    index): the oracle's dense array is bit-identical in exact mode"""
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, "o.bin")
+        O.run_ref_driver(workers=workers, op="reduce_to_index", gen="uniform", universe=universe, n=n, exact=1, out=out)
+        ref = np.fromfile(out, dtype=O.KV)
+    assert len(ref) == universe
+    mine = O.reduce_to_index(_rti_input("uniform", n, universe, 1), universe, O.OP_SUM_F64)
+    assert np.array_equal(mine, ref)
