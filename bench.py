@@ -353,6 +353,25 @@ def main():
                                      "step_share": {"partition_ms": rpart_ms / 3, "partition_launches_per_step": rpart_cnt / 3,
                                                     "count_ms": (rhist_ms + rsegc_ms) / 3, "aggregate_ms": agg_ms / 3,
                                                     "compact_ms": cmp_ms / 3, "nccl_alltoallv_ms": rx_ms / 3, "step_ms": r_step}}}
+        # ReduceByKey-uniform: the same operator where there is little to reduce (distinct ~ 0.45 n).  Guarded:
+        # an extra must never cost the headline line.
+        try:
+            u_ms = []
+            for it in range(1 + 2):
+                tg.ck(L.tg_gen_reduce_uniform(tg.h, d_rin, rank * rn, rn, SEED, ZIPF_UNIVERSE, 0))
+                tg.barrier()
+                tg.timer_start()
+                rp2, rc2 = C.c_void_p(), C.c_size_t()
+                tg.ck(L.tg_reduce_by_key(tg.h, C.byref(kvd), d_rin, rn, C.byref(rp2), C.byref(rc2)))
+                ms = max_over_ranks(tg.timer_stop(), world)
+                if it >= 1:
+                    u_ms.append(ms)
+            u_step = sum(u_ms) / len(u_ms)
+            extra["reduce_uniform"] = {"records_per_s": rn * world / (u_step / 1e3), "ms_per_step": u_step,
+                                       "distinct_out": int(sum_over_ranks(float(rc2.value), world)),
+                                       "workload": "reduce_pair_u64_f64_uniform_U2^26"}
+        except Exception as e:          # noqa: BLE001
+            extra["reduce_uniform"] = {"error": str(e)[:200]}
         tg.free(d_rin); tg.free(d_cdf)
 
     clocks = sampler.stop()
