@@ -22,6 +22,9 @@ namespace tgp {
 #ifndef TG_PF
 #define TG_PF 1
 #endif
+#ifndef TG_MATCH_MIX
+#define TG_MATCH_MIX 0   // 1: experiment, see rank_rows
+#endif
 #ifndef TG_LB_SEG
 #define TG_LB_SEG 8      // (a dominant segment's tiles still run concurrently at the tail of the list: keep the batch deep)
 #endif
@@ -155,7 +158,12 @@ __device__ __forceinline__ void rank_rows(const Item (&key)[ITEMS], u32 (&rank)[
         if (!FULL && p >= tile_valid) d = RADIX - 1;
         const u32 a = whist_w + d * 4;
         const u32 old = lds_u32(a);
+#if TG_MATCH_MIX
+        // experiment build (scripts/build_variant.sh "-DTG_MATCH_MIX=1"): every other row on the ADU pipe (match.any.sync)
+        const u32 peers = nomatch ? (~lt & (lt << 1 | 1u)) : ((i & 1) ? __match_any_sync(0xffffffffu, d) : match_digit8(d));
+#else
         const u32 peers = nomatch ? (~lt & (lt << 1 | 1u)) : match_digit8(d);
+#endif
         const u32 below = peers & lt;
         if (below == 0) sts_u32(a, old + __popc(peers));
         rank[i] = old + __popc(below);
