@@ -1,14 +1,15 @@
-// tg_partition.cuh — the stable single-pass multi-way partition kernel ("onesweep") shared by
-//   * the LSB radix sort            (digit = 8 key bits)                       tg_radix_sort.cu
-//   * the splitter classify/scatter (digit = destination worker by splitters)  tg_sample_sort.cu
-//   * the hash partition            (digit = Hash128to64(0,key) % p)           tg_reduce.cu
+// tg_partition.cuh — the stable multi-way (<= 256 buckets) partition pass shared by
+//   * the local sort                (digit = 8 key bits)                            tg_radix_sort.cu
+//   * the splitter classify/scatter (digit = destination worker by the splitters)   tg_sample_sort.cu
+//   * the hash aggregation          (digit = a byte of Hash128to64(0,key), or % p)  tg_reduce.cu
 //
-// One persistent CTA per SM walks tiles in static round-robin order.  A tile (64 KB) is staged into
-// shared memory by the TMA unit (cp.async.bulk + mbarrier, double buffered so the next tile lands while
-// the current one is processed), ranked stably with warp-synchronous match.any + warp-private counters,
-// positioned globally by a chained scan with batched decoupled look-back, reordered by digit inside the
+// Persistent CTAs walk a list of tiles in static round-robin order.  A tile (32-64 KB) is staged into shared memory by
+// the TMA unit (cp.async.bulk + mbarrier, double buffered: the next tile lands while the current one is processed), ranked
+// stably with warp-synchronous ballots + warp-private counters, positioned by a chained scan with batched decoupled
+// look-back over the tiles of its SEGMENT (the whole input for the plain pass; see tg_segmented.cuh for the chunked and
+// segmented passes whose tile lists never make a tile wait for a concurrently processed one), reordered by digit inside the
 // (re-used) landing buffer and written out so that consecutive threads write consecutive addresses.
-// HBM traffic: read n*s + write n*s + ~3 % look-back state.
+// HBM traffic: read n*s + write n*s + ~3 % scan state.
 #pragma once
 #include <stdlib.h>
 

@@ -3,10 +3,13 @@
 // Replaces the local sort of the reference's sample sort: SortNode::SortAndWriteToFile ->
 // sort_algorithm_(begin,end,cmp) = std::sort (api/sort.hpp:696-742, :789-796).
 //
-// One histogram kernel (all digit histograms from a single read of the input), one tiny scan kernel,
-// then one stable partition pass (tg_partition.cuh, "onesweep") per 8-bit digit, least significant
-// first.  Digit positions where every key has the same value are skipped (identity passes).
-// HBM traffic: n*s for the histogram + per executed pass n*s read + n*s write (s = item bytes).
+// Prefix sort (the fast path, prefix_sort_fast): one counting read (chunk histograms of the most significant key byte +
+// OR/AND of all keys), the pass on that byte as a chunked pass, the next K-1 non-constant bytes as segmented passes inside
+// its buckets (tg_segmented.cuh), and one finishing pass that orders the short runs of equal K-byte prefixes by the full
+// key (prefix_fixup_kernel); K = ceil((log2 n + 4) / 8).  8 + K*16 + 8 + 16 bytes per 8-byte key.
+// General path (few non-constant bytes, long runs of equal prefixes, small inputs): one histogram kernel (all digit
+// histograms from a single read), one tiny scan kernel, then one stable partition pass per non-constant 8-bit digit,
+// least significant first (chained scan).  n*s for the histogram + per pass n*s read + n*s write (s = item bytes).
 #include "tg_partition.cuh"
 #include "tg_keys.cuh"
 #include "tg_segmented.cuh"

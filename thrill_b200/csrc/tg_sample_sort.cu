@@ -6,12 +6,15 @@
 // ReceiveItems/SortAndWriteToFile local sort (:665-742) and the multiway merge of PushData (:216-271,
 // core/multiway_merge.hpp:30-116).
 //
-// GPU formulation (the "sorted runs" form named in the north star; same output contract):
-//   local LSB radix sort -> splitter bucket boundaries (classification of a sorted, stable shard is a
-//   set of p-1 positions: lower_bound by key + the number of equal-key items with global index <= the
-//   splitter's index) -> NCCL Alltoallv of the p contiguous ranges -> k-way merge of the p received runs.
-// The stand-alone classify+scatter kernel (tg_classify_scatter, for unsorted input, the literal
-// TransmitItems) and the k-way merge kernel are exported for parity tests and ncu captures.
+// GPU formulations (same output contract):
+//   default, the reference's own order: classify + stable scatter by the splitters (one chunked partition pass with the
+//     (key, global index) tie-break) -> NCCL Alltoallv -> local sort of what was received;
+//   TG_SORT_PIPELINE=merge, the "sorted runs" form named in the north star: local sort -> splitter bucket boundaries
+//     (classification of a sorted, stable shard is a set of p-1 positions: lower_bound by key + the number of equal-key
+//     items with global index <= the splitter's index) -> NCCL Alltoallv of the p contiguous ranges -> k-way merge of the p
+//     received runs.
+// The stand-alone classify+scatter (tg_classify_scatter, the literal TransmitItems) and the k-way merge (tg_kway_merge)
+// are exported for parity tests and ncu captures.
 #include <algorithm>
 #include <cmath>
 
