@@ -135,9 +135,11 @@ size_t tg_file_geometry(uint64_t num_items, uint32_t item_bytes, uint64_t start_
 
 /* ---- kernel-level entry points (parity tests, ncu captures) ------------------------------------------ */
 
-/* LSB radix sort of n items in place (result in d_items); d_tmp >= n*item_bytes scratch.  Replaces
+/* Stable local sort of n items in place (result in d_items); d_tmp >= n*item_bytes scratch.  Replaces
  * SortNode::SortAndWriteToFile's sort_algorithm_(begin,end,cmp) = std::sort (api/sort.hpp:696-742,
- * :789-796) and the common::RadixSort functor hook (common/radix_sort.hpp:147-162). */
+ * :789-796) and the common::RadixSort functor hook (common/radix_sort.hpp:147-162).  Radix sort on the
+ * non-constant key bytes: partition passes on the K most significant ones + one finishing pass on the runs
+ * of equal prefixes, or plain LSD passes where that does not apply. */
 int tg_radix_sort_local(tg_ctx* ctx, const tg_key_desc* desc, void* d_items, void* d_tmp, size_t n);
 
 /* Sample count and host-side splitter selection: common/reservoir_sampling.hpp:270-275 (eps = 0.1,
