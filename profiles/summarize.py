@@ -51,5 +51,51 @@ def kernel(path):
             print("    %10.3f  %s" % (v, h))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and sys.argv[1] in ("launches", "kernel"):
     {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2])
+
+
+def source(path, top=45):
+    """per source line: warp instructions executed and stall samples (ncu --page source with --import-source on),
+    first kernel of the report only"""
+    raw = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "cuda,sass"],
+                         capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    cur_file, hdr, per = None, None, collections.OrderedDict()
+    nk = 0
+    for r in rows:
+        if not r:
+            continue
+        if r[0] == "File Path":
+            cur_file = r[1].split("/")[-1]
+            continue
+        if r[0] == "Function Name":
+            continue
+        if r[0] == "Kernel Name":
+            nk += 1
+            if nk > 1:
+                break
+            continue
+        if r[0] == "Line No":
+            hdr = r
+            ii, si = hdr.index("Instructions Executed"), hdr.index("# Samples")
+            continue
+        if hdr is None or len(r) < len(hdr) - 2:
+            continue
+        if r[0].isdigit():           # a source line row: totals of its SASS
+            key = (cur_file, int(r[0]))
+            try:
+                ent = per.setdefault(key, [0, 0, r[1].strip()[:110]])
+                ent[0] += int(r[ii]); ent[1] += int(r[si])
+            except ValueError:
+                pass
+    tot_i = sum(v[0] for v in per.values()) or 1
+    tot_s = sum(v[1] for v in per.values()) or 1
+    print("total warp instructions %d, stall samples %d" % (tot_i, tot_s))
+    print("%-22s %6s %6s  %s" % ("file:line", "inst%", "smpl%", "source"))
+    for (f, ln), v in sorted(per.items(), key=lambda kv: -kv[1][0])[:top]:
+        print("%-22s %6.2f %6.2f  %s" % ("%s:%d" % (f, ln), 100.0 * v[0] / tot_i, 100.0 * v[1] / tot_s, v[2]))
+
+
+if __name__ == "__main__" and len(sys.argv) > 2 and sys.argv[1] == "source":
+    source(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 45)

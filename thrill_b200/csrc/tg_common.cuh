@@ -15,7 +15,8 @@
 typedef unsigned long long u64;
 typedef unsigned int u32;
 
-#define TG_NUM_WS 18
+#define TG_NUM_WS 20
+#define TG_MAX_RANKS 16
 
 struct tg_ctx {
     int device = 0, rank = 0, nranks = 1;
@@ -44,6 +45,18 @@ struct tg_ctx {
     struct ProfEv { int cls; cudaEvent_t a, b; };
     std::vector<ProfEv> prof_events;
     std::vector<cudaEvent_t> prof_pool;
+    // exchange window (tg_exchange.cu): the buffer the peers of a collective operator store this worker's share of the
+    // Alltoallv into, directly over NVLink (P2P stores from the partition kernel).  peer[r] = rank r's window as mapped
+    // into this process (CUDA IPC between processes, the raw pointer + peer access between worker threads of one process).
+    struct XWin {
+        void* base = nullptr;
+        size_t cap = 0;                        // bytes; the same on every rank (grown collectively)
+        void* peer[TG_MAX_RANKS] = { nullptr };
+        bool ipc_open[TG_MAX_RANKS] = { false };
+        void** d_peer = nullptr;               // device scratch: [0..p) destination base pointers of the current exchange
+        int mode = -1;                         // -1 not negotiated yet, 0 = NCCL send/recv, 1 = P2P stores
+    } xwin;
+    int spec_top_bit = 64;                     // prefix sort: expected position of the most significant varying key bit
     // result of the last *_file operator, fetched by tg_fetch_output
     void* out_ptr = nullptr;
     size_t out_items = 0;
@@ -54,7 +67,7 @@ struct tg_ctx {
 enum { WS_SORT_TMP = 0, WS_SORT_STATUS = 1, WS_SORT_HIST = 2, WS_XCHG_SEND = 3, WS_XCHG_RECV = 4,
        WS_MISC = 5, WS_TABLE = 6, WS_OUT = 7, WS_IN = 8, WS_AUX = 9, WS_AUX2 = 10, WS_SAMPLES = 11,
        WS_SEG_TILES = 12, WS_SEG_TABLES = 13, WS_SORT_STATUS2 = 14,
-       WS_SORT_HIST2 = 15, WS_SEG_TILES2 = 16, WS_DENSE = 17 };
+       WS_SORT_HIST2 = 15, WS_SEG_TILES2 = 16, WS_DENSE = 17, WS_XCTL = 18, WS_REC = 19 };
 
 int tg_set_error(tg_ctx* ctx, int status, const char* fmt, ...);
 int tg_ws_get(tg_ctx* ctx, int slot, size_t bytes, void** out);

@@ -3,6 +3,8 @@
 
 #include "tg_common.cuh"
 
+namespace tgp { void xwin_release(tg_ctx* ctx); }
+
 int tg_set_error(tg_ctx* ctx, int status, const char* fmt, ...) {
     if (ctx) {
         va_list ap;
@@ -162,6 +164,7 @@ int tg_shutdown(tg_ctx* ctx) {
     if (!ctx) return TG_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    tgp::xwin_release(ctx);
     if (ctx->comm) ncclCommDestroy(ctx->comm);
     for (auto& kv : ctx->allocs) cudaFree(kv.first);
     for (int i = 0; i < TG_NUM_WS; ++i)

@@ -49,6 +49,7 @@ struct RadixDigit {
     int word, shift;
     u32 flip;
     static constexpr bool kStoreDigit = false;      // cheap to recompute in the write-out
+    __device__ __forceinline__ void init() {}
     template <class Item>
     __device__ __forceinline__ u32 operator()(const Item& v, u32) const {
         return ((u32)(item_word(v, word) >> shift) & (RADIX - 1)) ^ flip;
@@ -100,7 +101,8 @@ __device__ __forceinline__ u32 match_digit8(u32 d) {
 }
 
 // tile geometry of one launch configuration: THREADS threads, each owning IPT items of WORDS 8-byte words
-template <int WORDS, int THREADS, int IPT, bool TMA = true, bool STORE = true>
+constexpr int PEER_MAX = 32;        // destinations of a partition pass that stores into peer windows (<= TG_MAX_RANKS used)
+template <int WORDS, int THREADS, int IPT, bool TMA = true, bool STORE = true, bool PEER = false>
 struct SweepCfg {
     static constexpr int ITEM_BYTES = 8 * WORDS;
     static constexpr int ITEMS = IPT;
@@ -108,11 +110,11 @@ struct SweepCfg {
     static constexpr int TILE_BYTES = TILE * ITEM_BYTES;
     static constexpr int NWARPS = THREADS / 32;
     // 2 landing/exchange buffers | warp counters [NWARPS][RADIX] | goff [RADIX] | warp_tot [16] | mbar [2] | dig [TILE]
-    static constexpr int BUF_BYTES = TILE_BYTES + 16;       // + one 16-byte granule: tiles that start at an odd 8-byte item
+    static constexpr int BUF_BYTES = TILE_BYTES + (WORDS == 1 ? 16 : 0);      // + one 16-byte granule: tiles that start at an odd 8-byte item
     static constexpr int NBUF = TMA ? 2 : 1;                // landing + exchange, or the exchange buffer alone
     // buffers | warp counters [NWARPS][RADIX] | goff [RADIX] | warp_tot [16] | mbar [2] | digit bytes [TILE] (only if the digit
     // function's result is kept, kStoreDigit) | slack
-    static constexpr int SMEM = NBUF * BUF_BYTES + NWARPS * RADIX * 4 + RADIX * 4 + 64 + 16 + (STORE ? TILE : 0) + 128;
+    static constexpr int SMEM = NBUF * BUF_BYTES + NWARPS * RADIX * (int)sizeof(unsigned short) + RADIX * 4 + 64 + 16 + (STORE ? TILE : 0) + (PEER ? PEER_MAX * 8 : 0) + 128;
 };
 
 // exclusive scan of npass digit histograms -> global bases; skip[p] = 1 if one bin holds everything
@@ -145,6 +147,15 @@ __device__ __forceinline__ u32 lds_u32(u32 addr) {
     return v;
 }
 __device__ __forceinline__ void sts_u32(u32 addr, u32 v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+// the warp-private digit counters are 16-bit (a tile holds < 65536 items): half the shared memory, which is what lets a third
+// CTA of the 16-byte-item configuration fit on an SM
+typedef unsigned short cnt_t;
+__device__ __forceinline__ u32 lds_cnt(u32 addr) {
+    u32 v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_cnt(u32 addr, u32 v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 
 // stable rank of the warp's ITEMS rows inside the (warp, digit) groups.  Every lane reads its group's counter, the
 // lowest lane of the group bumps it (same warp, program order: the read precedes the write).  whist_w = shared
@@ -157,8 +168,8 @@ __device__ __forceinline__ void rank_rows(const Item (&key)[ITEMS], u32 (&rank)[
         const u32 p = pos0 + i * 32;
         u32 d = fn(key[i], tile_base + p);
         if (!FULL && p >= tile_valid) d = RADIX - 1;
-        const u32 a = whist_w + d * 4;
-        const u32 old = lds_u32(a);
+        const u32 a = whist_w + d * (u32)sizeof(cnt_t);
+        const u32 old = lds_cnt(a);
 #if TG_MATCH_MIX
         // experiment build (scripts/build_variant.sh "-DTG_MATCH_MIX=1"): every other row on the ADU pipe (match.any.sync)
         const u32 peers = nomatch ? (~lt & (lt << 1 | 1u)) : ((i & 1) ? __match_any_sync(0xffffffffu, d) : match_digit8(d));
@@ -166,7 +177,7 @@ __device__ __forceinline__ void rank_rows(const Item (&key)[ITEMS], u32 (&rank)[
         const u32 peers = nomatch ? (~lt & (lt << 1 | 1u)) : match_digit8(d);
 #endif
         const u32 below = peers & lt;
-        if (below == 0) sts_u32(a, old + __popc(peers));
+        if (below == 0) sts_cnt(a, old + __popc(peers));
         rank[i] = old + __popc(below);
         if (STORE) rank[i] |= d << 16;
         __syncwarp();
@@ -188,17 +199,20 @@ struct SegList {
 
 // One tile: rank -> per-digit counts (published for the chained scan) -> scatter into the exchange buffer while
 // the look-back loads are in flight -> resolve the look-back -> coalesced write-out.
-template <int WORDS, int THREADS, int IPT, int MINB, class DigitFn, bool SEG, bool DBG = false, bool TMA = true>
+// PEER: the buckets are destination workers; bucket d is written to dbase[d][position], where dbase[d] points into worker
+// d's exchange window (mapped peer memory: the stores travel over NVLink) biased so that `position` is the position the
+// plain pass would have used in `out` — the Alltoallv of the reference's MixStream exchange happens inside the pass.
+template <int WORDS, int THREADS, int IPT, int MINB, class DigitFn, bool SEG, bool DBG = false, bool TMA = true, bool PEER = false>
 __global__ void __launch_bounds__(THREADS, MINB)
 partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename ItemT<WORDS>::type* __restrict__ out,
                  u32 n, const DigitFn fn_param, const u32* __restrict__ gbase, u32* __restrict__ status, const SegList sl,
-                 int dbg) {
+                 int dbg, typename ItemT<WORDS>::type* const* __restrict__ dbase) {
     // DBG instantiations (TG_SWEEP_DEBUG, timing experiments only, results are wrong): dbg bit0 = no look-back wait,
     // bit1 = no matching, bit2 = linear instead of scattered write-out, bit3 = no write-out
     typedef typename ItemT<WORDS>::type Item;
     // TMA = false: no landing buffer and no bulk copies; the items are loaded straight into registers (coalesced 8/16-byte
     // loads) and several small CTAs per SM hide each other's load latency and barriers instead of the double buffer
-    typedef SweepCfg<WORDS, THREADS, IPT, TMA, DigitFn::kStoreDigit> C;
+    typedef SweepCfg<WORDS, THREADS, IPT, TMA, DigitFn::kStoreDigit, PEER> C;
     constexpr int ITEMS = C::ITEMS, TILE = C::TILE, NWARPS = C::NWARPS;
     // look-back batch (predecessors fetched concurrently): inside a segment the predecessor finished a wave ago, one or two
     // loads find its inclusive prefix; the plain chained scan over concurrently processed tiles needs a deep batch
@@ -210,17 +224,19 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Item* const buf0 = reinterpret_cast<Item*>(smem_raw);
     Item* const buf1 = reinterpret_cast<Item*>(smem_raw + (C::NBUF - 1) * C::BUF_BYTES);
-    u32* const whist = reinterpret_cast<u32*>(smem_raw + C::NBUF * C::BUF_BYTES);      // [NWARPS][RADIX]
-    u32* const goff = whist + NWARPS * RADIX;                                    // [RADIX]
+    cnt_t* const whist = reinterpret_cast<cnt_t*>(smem_raw + C::NBUF * C::BUF_BYTES);  // [NWARPS][RADIX]
+    u32* const goff = reinterpret_cast<u32*>(whist + NWARPS * RADIX);            // [RADIX]
     u32* const warp_tot = goff + RADIX;                                          // [16]
     u64* const mbar = reinterpret_cast<u64*>(warp_tot + 16);                     // [2]
     unsigned char* const dig = reinterpret_cast<unsigned char*>(mbar + 2);       // [TILE], only if kStoreDigit
+    Item** const dptr = reinterpret_cast<Item**>(dig + (DigitFn::kStoreDigit ? TILE : 0));      // [PEER_MAX], only if PEER
 
-    const DigitFn fn = fn_param;
+    DigitFn fn = fn_param;
+    fn.init();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 num_tiles = SEG ? sl.num_tiles : (n + TILE - 1) / TILE;
     const u32 lt = lanemask_lt();
-    u32* const whist_w = whist + warp * RADIX;
+    cnt_t* const whist_w = whist + warp * RADIX;
     const u32 whist_w_a = smem_u32(whist_w);
     const u32 wbase = warp * 32 * ITEMS;
 
@@ -253,6 +269,7 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
         mbar_init(&mbar[1], 1);
         mbar_fence_init();
     }
+    if (PEER && tid < PEER_MAX) dptr[tid] = dbase[tid];
     __syncthreads();
 
     u32 j = blockIdx.x;
@@ -291,7 +308,7 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
         }
         // zero this warp's private digit counters
 #pragma unroll
-        for (int i = 0; i < RADIX / 32; ++i) whist_w[i * 32 + lane] = 0;
+        for (int i = 0; i < RADIX / 64; ++i) reinterpret_cast<u32*>(whist_w)[i * 32 + lane] = 0;
 
         // ---- items to registers: warp w owns tile positions [w*32*ITEMS, (w+1)*32*ITEMS), round-striped.
         // Positions past the end of a partial tile get digit RADIX-1: the stable ranking puts them behind every
@@ -326,7 +343,7 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
 
         // ---- per-digit tile count; publish PARTIAL as early as possible; start the look-back loads
         u32 count = 0, my_start = 0;
-        u32 lbv[PF ? LB : 1];
+        u32 lbv[(PF && !SEG) ? LB : 1];
         const u32 my_gb = tid < RADIX ? __ldg(&gb[tid]) : 0u;      // (requested early: needed after the look-back)
         u32* const my_status = status + (size_t)ti.row * RADIX + tid;       // predecessor k: my_status - k * RADIX
         if (tid < RADIX) {
@@ -335,7 +352,11 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
             u32 pub = count;
             if (!full_tile && tid == RADIX - 1) pub -= (u32)TILE - tile_valid;      // padding is not data
             st_relaxed_u32(my_status, pub | (ti.idx == 0 ? FLAG_INCL : FLAG_PARTIAL));
-            if (PF) {
+            if (SEG) {
+                // inside a segment the predecessor finished a wave of CTAs ago: one load nearly always finds its inclusive prefix
+                lbv[0] = ti.idx > 0 ? ld_relaxed_u32(my_status - RADIX) : FLAG_INCL;
+            }
+            else if (PF) {
 #pragma unroll
                 for (int k = 0; k < LB; ++k)
                     lbv[PF ? k : 0] = ((u32)(k + 1) <= ti.idx) ? ld_relaxed_u32(my_status - (size_t)(k + 1) * RADIX) : FLAG_INCL;
@@ -357,7 +378,7 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
 #pragma unroll
             for (int w = 0; w < NWARPS; ++w) {
                 u32 c = whist[w * RADIX + tid];
-                whist[w * RADIX + tid] = off;
+                whist[w * RADIX + tid] = (cnt_t)off;
                 off += c;
             }
         }
@@ -368,14 +389,14 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) {
                 u32 d = fn(key[i], 0);
-                buf[lds_u32(whist_w_a + d * 4) + rank[i]] = key[i];
+                buf[lds_cnt(whist_w_a + d * (u32)sizeof(cnt_t)) + rank[i]] = key[i];
             }
         }
         else {
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) {
                 u32 d = rank[i] >> 16;
-                u32 q = lds_u32(whist_w_a + d * 4) + (rank[i] & 0xffffu);
+                u32 q = lds_cnt(whist_w_a + d * (u32)sizeof(cnt_t)) + (rank[i] & 0xffffu);
                 buf[q] = key[i];
                 if (DigitFn::kStoreDigit) dig[q] = (unsigned char)d;
             }
@@ -389,7 +410,18 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
                 u32 back = 1;              // distance of the next predecessor to consume
                 bool done = false;
                 u32 v[LB];
-                if (PF) {
+                if (SEG) {
+                    // fast path: the prefetched predecessor carries an inclusive prefix.  Otherwise (tiles of a dominant segment that
+                    // run at the same time) continue with batches of LB predecessors per round trip.
+                    if (lbv[0] & FLAG_INCL) { excl = lbv[0] & VALUE_MASK; done = true; }
+                    else {
+                        v[0] = lbv[0];
+#pragma unroll
+                        for (int k = 1; k < LB; ++k)
+                            v[k] = (back + k <= ti.idx) ? ld_relaxed_u32(my_status - (size_t)(back + k) * RADIX) : FLAG_INCL;
+                    }
+                }
+                else if (PF) {
 #pragma unroll
                     for (int k = 0; k < LB; ++k) v[k] = lbv[PF ? k : 0];
                 }
@@ -398,7 +430,7 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
                     for (int k = 0; k < LB; ++k)
                         v[k] = (back + k <= ti.idx) ? ld_relaxed_u32(my_status - (size_t)(back + k) * RADIX) : FLAG_INCL;
                 }
-                while (true) {
+                while (!done) {
                     bool stalled = false;
 #pragma unroll
                     for (int k = 0; k < LB; ++k) {
@@ -431,6 +463,7 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
                     u32 d = DigitFn::kStoreDigit ? (u32)dig[i * THREADS + tid] : fn(v, 0);
                     if (DBG && (dbg & 8)) continue;
                     if (DBG && (dbg & 4)) out[tile_base + (u32)(i * THREADS + tid)] = v;
+                    else if (PEER) dptr[d][goff[d] + (u32)(i * THREADS + tid)] = v;
                     else out[goff[d] + (u32)(i * THREADS + tid)] = v;
                 }
             }
@@ -440,7 +473,8 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
                     if ((u32)(i * THREADS + tid) < tile_valid) {
                         Item v = bufp[i * THREADS];
                         u32 d = DigitFn::kStoreDigit ? (u32)dig[i * THREADS + tid] : fn(v, 0);
-                        out[goff[d] + (u32)(i * THREADS + tid)] = v;
+                        if (PEER) dptr[d][goff[d] + (u32)(i * THREADS + tid)] = v;
+                        else out[goff[d] + (u32)(i * THREADS + tid)] = v;
                     }
                 }
             }
@@ -484,13 +518,13 @@ inline int sweep_debug() {
     return f;
 }
 
-template <int WORDS, int THREADS, int WPT, int MINB, class DigitFn, bool SEG = false, bool DBG = false, bool TMA = true>
+template <int WORDS, int THREADS, int WPT, int MINB, class DigitFn, bool SEG = false, bool DBG = false, bool TMA = true, bool PEER = false>
 int launch_partition_v(tg_ctx* ctx, const void* in, void* out, u32 n, const DigitFn& fn, const u32* gbase, u32* status,
-                       const SegList& sl = SegList{ nullptr, nullptr, 0 }) {
+                       const SegList& sl = SegList{ nullptr, nullptr, 0 }, typename ItemT<WORDS>::type* const* dbase = nullptr) {
     typedef typename ItemT<WORDS>::type Item;
     constexpr int IPT = WPT / WORDS;
-    typedef SweepCfg<WORDS, THREADS, IPT, TMA, DigitFn::kStoreDigit> C;
-    auto kern = partition_kernel<WORDS, THREADS, IPT, MINB, DigitFn, SEG, DBG, TMA>;
+    typedef SweepCfg<WORDS, THREADS, IPT, TMA, DigitFn::kStoreDigit, PEER> C;
+    auto kern = partition_kernel<WORDS, THREADS, IPT, MINB, DigitFn, SEG, DBG, TMA, PEER>;
     int ctas_per_sm = 0;
     auto it = ctx->kernel_cfg.find((const void*)kern);
     if (it != ctx->kernel_cfg.end()) ctas_per_sm = it->second;
@@ -506,7 +540,7 @@ int launch_partition_v(tg_ctx* ctx, const void* in, void* out, u32 n, const Digi
     if (num_tiles == 0) return TG_OK;
     int grid = ctx->sm_count * ctas_per_sm;
     if (grid > (int)num_tiles) grid = (int)num_tiles;
-    TG_LAUNCH_T(ctx, TG_K_PARTITION, kern, grid, THREADS, C::SMEM, (const Item*)in, (Item*)out, n, fn, gbase, status, sl, DBG ? sweep_debug() : 0);
+    TG_LAUNCH_T(ctx, TG_K_PARTITION, kern, grid, THREADS, C::SMEM, (const Item*)in, (Item*)out, n, fn, gbase, status, sl, DBG ? sweep_debug() : 0, dbase);
     return TG_OK;
 }
 
@@ -562,6 +596,19 @@ int launch_partition_seg(tg_ctx* ctx, const void* in, void* out, u32 n, const Di
     case 9: return launch_partition_v<WORDS, 256, 16, 4, DigitFn, true, false, false>(ctx, in, out, n, fn, nullptr, status, sl);
     case 10: return launch_partition_v<WORDS, 512, 16, 2, DigitFn, true, false, false>(ctx, in, out, n, fn, nullptr, status, sl);
     default: return launch_partition_v<WORDS, 512, 16, 1, DigitFn, true>(ctx, in, out, n, fn, nullptr, status, sl);
+    }
+}
+
+// one segmented partition pass whose buckets are destination workers: bucket d goes to dbase[d] (device array of PEER_MAX
+// pointers into the peers' exchange windows, see tg_exchange.cuh)
+template <int WORDS, class DigitFn>
+int launch_partition_peer(tg_ctx* ctx, const void* in, u32 n, const DigitFn& fn, u32* status, const SegList& sl,
+                          typename ItemT<WORDS>::type* const* dbase) {
+    switch (sweep_cfg()) {
+    case 1: return launch_partition_v<WORDS, 256, 16, 2, DigitFn, true, false, true, true>(ctx, in, nullptr, n, fn, nullptr, status, sl, dbase);
+    case 0: return launch_partition_v<WORDS, 512, 16, 1, DigitFn, true, false, true, true>(ctx, in, nullptr, n, fn, nullptr, status, sl, dbase);
+    case 2: return launch_partition_v<WORDS, 256, 16, 3, DigitFn, true, false, true, true>(ctx, in, nullptr, n, fn, nullptr, status, sl, dbase);
+    default: return tg_set_error(ctx, TG_ERR_ARG, "TG_SWEEP_CFG=%d has no peer-store variant (use 0, 1 or 2, or TG_EXCHANGE=nccl)", sweep_cfg());
     }
 }
 

@@ -346,12 +346,11 @@ int run_segmented_passes(tg_ctx* ctx, const PassList& pl, const int* pos, int np
 
 // finishing pass of the prefix sort over src -> dst; *ok = no group was too long
 template <int WORDS>
-int run_fixup(tg_ctx* ctx, const tg_key_desc* desc, bool plain_u64, int pass0, const void* src, void* dst, size_t n, u32* d_fail,
+int run_fixup(tg_ctx* ctx, const tg_key_desc* desc, bool plain_u64, const PrefixMask& pm, const void* src, void* dst, size_t n, u32* d_fail,
               bool* ok) {
     typedef typename ItemT<WORDS>::type Item;
     KeyView kv;
     if (make_key_view(desc, &kv) != TG_OK) return tg_set_error(ctx, TG_ERR_ARG, "radix sort: unsupported key descriptor");
-    PrefixMask pm = prefix_mask(desc, pass0);
     const u32 grid = (u32)((n + FIX_TILE - 1) / FIX_TILE);
     TG_CUDA(ctx, cudaMemsetAsync(d_fail, 0, 4, ctx->stream));
     if (plain_u64 && !desc->descending)
@@ -365,10 +364,12 @@ int run_fixup(tg_ctx* ctx, const tg_key_desc* desc, bool plain_u64, int pass0, c
     return TG_OK;
 }
 
-// Speculative fast path of the prefix sort: assumes the most significant key byte is an active digit with many
-// values.  One read (chunk histograms of that digit + OR/AND of the keys), the pass on it as a segmented pass over the
-// chunks, the other K-1 prefix digits inside its buckets, the finishing pass.  *taken = the items in *src are sorted;
-// otherwise *src holds a permutation of the input and the caller runs the general path.
+// Speculative fast path of the prefix sort: assumes the position of the most significant varying key bit (ctx->spec_top_bit for
+// integer keys held in one item word — a worker of a multi-GPU sort knows it from its splitters, a single worker learns it from
+// the OR/AND of the previous sort — the most significant key byte otherwise) and that the digit below it has many values.  One
+// read (chunk histograms of that digit + OR/AND of the keys), the pass on it as a segmented pass over the chunks, the other K-1
+// prefix digits inside its buckets, the finishing pass.  *taken = the items in *src are sorted; otherwise *src holds a
+// permutation of the input and the caller runs the general path.
 template <int WORDS>
 int prefix_sort_fast(tg_ctx* ctx, const tg_key_desc* desc, const PassList& pl, bool plain_u64, size_t n, void** src, void** dst,
                      bool* taken) {
@@ -378,7 +379,21 @@ int prefix_sort_fast(tg_ctx* ctx, const tg_key_desc* desc, const PassList& pl, b
     if (!prefix_sort_enabled() || !segmented_enabled() || pl.npass < K + 2 || n < (1u << 15)) return TG_OK;
     if (ctx->prefix_sort_penalty > 0) return TG_OK;          // counted down by the general path
     if (ctx->prefix_spec_penalty > 0) { ctx->prefix_spec_penalty--; return TG_OK; }
-    const int top = pl.npass - 1;
+    // integer key inside one item word: digits at bit granularity (a worker's key range need not start at a byte boundary)
+    const bool bitwise = desc->key_kind == TG_KEY_UINT_LE && (desc->key_offset & 7) + desc->key_bytes <= 8;
+    const int kb0 = 8 * (int)(desc->key_offset & 7), kbits = 8 * (int)desc->key_bytes;
+    PassList pp = pl;                // the K prefix digits, least significant first (pp.npass = K)
+    int tb = kbits;
+    if (bitwise) {
+        tb = ctx->spec_top_bit < kbits ? ctx->spec_top_bit : kbits;
+        if ((tb + 7) / 8 < K + 2 || tb - 8 * K < 0) return TG_OK;          // few varying bits: plain LSD passes are as cheap
+        pp.npass = K;
+        for (int i = 0; i < K; ++i) {
+            pp.word[i] = (unsigned char)(desc->key_offset / 8);
+            pp.shift[i] = (unsigned char)(kb0 + tb - 8 * (K - i));
+        }
+    }
+    const int top = bitwise ? K - 1 : pl.npass - 1;
     const u32 tile = tile_items<WORDS>();
     const ChunkGeom cg = chunk_geometry<WORDS>(ctx, n);
     const u32 chunk_items = cg.chunk_items;
@@ -398,7 +413,7 @@ int prefix_sort_fast(tg_ctx* ctx, const tg_key_desc* desc, const PassList& pl, b
     u64* h_init = h_orand + 512;                 // separate pinned words: read by the H2D copy below
     for (int w = 0; w < 2; ++w) { h_init[2 * w] = 0; h_init[2 * w + 1] = ~0ull; }
     TG_CUDA(ctx, cudaMemcpyAsync(orand, h_init, 32, cudaMemcpyHostToDevice, ctx->stream));
-    const RadixDigit top_fn = { (int)pl.word[top], (int)pl.shift[top], pl.flip };
+    const RadixDigit top_fn = { (int)pp.word[top], (int)pp.shift[top], pl.flip };
     TG_LAUNCH_T(ctx, TG_K_RADIX_HIST, (chunk_hist_kernel<WORDS, RadixDigit, true>), nchunks, 512, 0, (const Item*)*src, (u32)n, chunk_items,
                 top_fn, chunkcount, orand);
     TG_LAUNCH(ctx, chunk_scan_kernel, 1, 4 * RADIX, 0, chunkcount, nchunks, totals, gbase_top, chunkbase);
@@ -415,30 +430,49 @@ int prefix_sort_fast(tg_ctx* ctx, const tg_key_desc* desc, const PassList& pl, b
     TG_CUDA(ctx, cudaMemsetAsync(cstatus, 0, (size_t)ctotal * RADIX * 4, ctx->stream));
     TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 
-    // which digit positions are active (not constant over all keys), least significant first
-    int active[MAX_PASSES], nactive = 0;
-    for (int p = 0; p < pl.npass; ++p) {
-        const u64 diff = h_orand[2 * pl.word[p]] ^ h_orand[2 * pl.word[p] + 1];
-        if ((diff >> pl.shift[p]) & 0xffu) active[nactive++] = p;
-    }
     int nonempty = 0;
     for (int d = 0; d < RADIX; ++d) nonempty += h_totals[d] ? 1 : 0;
-    if (nactive < K + 2 || active[nactive - 1] != top || nonempty < 32) {
-        ctx->prefix_spec_penalty = 8;         // the guess was wrong for this kind of input: do not pay for it every time
-        return TG_OK;
+    int prefix_pos[MAX_PASSES];      // indices into pp of the K-1 lower prefix digits, least significant first
+    PrefixMask pm = { 0, 0 };
+    if (bitwise) {
+        const int w = pp.word[0];
+        const u64 kmask = kbits >= 64 ? ~0ull : (((1ull << kbits) - 1) << kb0);
+        const u64 diff = (h_orand[2 * w] ^ h_orand[2 * w + 1]) & kmask;
+        const int tb_act = diff ? 64 - __builtin_clzll(diff) - kb0 : 0;          // most significant varying key bit + 1
+        if (tb_act != tb) ctx->spec_top_bit = tb_act > 8 ? tb_act : 8;           // what the next sort on this ctx should assume
+        if (tb_act > tb || nonempty < 32) {
+            // bits above the assumed top digit vary (this is not a most-significant-digit pass), or the digit has few values
+            if (tb_act > tb || (tb_act + 7) / 8 < K + 2) ctx->prefix_spec_penalty = tb_act > tb ? 0 : 8;
+            return TG_OK;
+        }
+        for (int i = 0; i < K - 1; ++i) prefix_pos[i] = i;
+        pm.lo = (kmask >> kb0) & ~((1ull << (pp.shift[0] - kb0)) - 1);            // canonical key = the key value (tg_keys.cuh)
+    }
+    else {
+        // which digit positions are active (not constant over all keys), least significant first
+        int active[MAX_PASSES], nactive = 0;
+        for (int p = 0; p < pl.npass; ++p) {
+            const u64 diff = h_orand[2 * pl.word[p]] ^ h_orand[2 * pl.word[p] + 1];
+            if ((diff >> pl.shift[p]) & 0xffu) active[nactive++] = p;
+        }
+        if (nactive < K + 2 || active[nactive - 1] != top || nonempty < 32) {
+            ctx->prefix_spec_penalty = 8;         // the guess was wrong for this kind of input: do not pay for it every time
+            return TG_OK;
+        }
+        for (int i = 0; i < K - 1; ++i) prefix_pos[i] = active[nactive - K + i];
+        pm = prefix_mask(desc, active[nactive - K]);
     }
     // (1) most significant digit: segmented pass over the chunks
     {
         SegList sl = { d_ctiles, chunkbase, ctotal };
-        RadixDigit fn = { (int)pl.word[top], (int)pl.shift[top], pl.flip };
-        TG_TRY((launch_partition_seg<WORDS, RadixDigit>(ctx, *src, *dst, (u32)n, fn, cstatus, sl)));
+        TG_TRY((launch_partition_seg<WORDS, RadixDigit>(ctx, *src, *dst, (u32)n, top_fn, cstatus, sl)));
         void* t = *src; *src = *dst; *dst = t;
     }
     // (2) the other K-1 prefix digits inside the buckets of (1)
-    TG_TRY((run_segmented_passes<WORDS>(ctx, pl, active + (nactive - K), K - 1, h_totals, gbase_top, n, src, dst)));
+    TG_TRY((run_segmented_passes<WORDS>(ctx, pp, prefix_pos, K - 1, h_totals, gbase_top, n, src, dst)));
     // (3) finishing pass
     bool ok = false;
-    TG_TRY((run_fixup<WORDS>(ctx, desc, plain_u64, active[nactive - K], *src, *dst, n, fail, &ok)));
+    TG_TRY((run_fixup<WORDS>(ctx, desc, plain_u64, pm, *src, *dst, n, fail, &ok)));
     if (ok) {
         void* t = *src; *src = *dst; *dst = t;
         *taken = true;
@@ -523,7 +557,7 @@ int radix_sort_impl(tg_ctx* ctx, const tg_key_desc* desc, const PassList& pl, vo
         else
             for (int a = nactive - K; a < nactive; ++a) TG_TRY(run_pass(active[a]));
         bool ok = false;
-        TG_TRY((run_fixup<WORDS>(ctx, desc, plain_u64, active[nactive - K], src, dst, n, fail, &ok)));
+        TG_TRY((run_fixup<WORDS>(ctx, desc, plain_u64, prefix_mask(desc, active[nactive - K]), src, dst, n, fail, &ok)));
         if (ok) {
             void* t = src; src = dst; dst = t;
             done = true;

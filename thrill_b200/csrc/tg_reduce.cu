@@ -19,6 +19,7 @@
 
 #include "tg_partition.cuh"
 #include "tg_segmented.cuh"
+#include "tg_exchange.cuh"
 
 using namespace tgp;
 
@@ -159,6 +160,7 @@ compact_kernel(const ulonglong2* __restrict__ tab, u64 cap, ulonglong2* __restri
 struct HashDigit {
     u32 p;
     static constexpr bool kStoreDigit = true;
+    __device__ __forceinline__ void init() {}
     __device__ __forceinline__ u32 operator()(const ulonglong2& v, u32) const { return (u32)(key_hash(v.x) % p); }
 };
 
@@ -229,6 +231,7 @@ constexpr size_t AGG_MIN_ITEMS = 1u << 18;         // below: the HBM table alone
 struct HashLevelDigit {
     int shift;
     static constexpr bool kStoreDigit = true;
+    __device__ __forceinline__ void init() {}
     __device__ __forceinline__ u32 operator()(const ulonglong2& v, u32) const { return (u32)(key_hash(v.x) >> shift) & (RADIX - 1); }
 };
 
@@ -581,6 +584,7 @@ struct RangeDigit {
     u64 size;
     u32 p;
     static constexpr bool kStoreDigit = true;
+    __device__ __forceinline__ void init() {}
     __device__ __forceinline__ u32 operator()(const ulonglong2& v, u32) const {
         return v.x < size ? (u32)(v.x * p / size) : p - 1;
     }
@@ -653,44 +657,13 @@ int tg_reduce_by_key(tg_ctx* ctx, const tg_kv_desc* desc, const void* d_in, size
         *out_n = (size_t)m;
         return TG_OK;
     }
-    const void* d_post_in = d_pre;
-    u64 m_post = m;
-    if (p > 1) {
-        if (m >= (1u << 30)) return tg_set_error(ctx, TG_ERR_TOO_LARGE, "reduce: %llu partial aggregates", m);
-        // partition by Hash128to64(0,key) % p, exchange (replaces the MixStream writers, :109-114)
-        void* d_send;
-        TG_TRY(tg_ws_get(ctx, WS_XCHG_SEND, (m + 2) * 16, &d_send));
-        HashDigit fn = { (u32)p };
-        u32* d_counts = nullptr;
-        TG_TRY((partition_chunked<2, HashDigit>(ctx, d_pre, d_send, m, fn, &d_counts, nullptr)));
-        u32* hc = (u32*)ctx->pinned;
-        TG_CUDA(ctx, cudaMemcpyAsync(hc, d_counts, RADIX * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        std::vector<u64> send_cnt(p), send_off(p + 1, 0);
-        for (int r = 0; r < p; ++r) { send_cnt[r] = hc[r]; send_off[r + 1] = send_off[r] + send_cnt[r]; }
-        u64* h = (u64*)ctx->pinned;
-        u64* d_ctl;
-        TG_TRY(tg_ws_get(ctx, WS_MISC, 1 << 16, (void**)&d_ctl));
-        for (int r = 0; r < p; ++r) h[r] = send_cnt[r];
-        TG_CUDA(ctx, cudaMemcpyAsync(d_ctl, h, 8 * p, cudaMemcpyHostToDevice, ctx->stream));
-        TG_NCCL(ctx, ncclAllGather(d_ctl, d_ctl + 64, p, ncclUint64, ctx->comm, ctx->stream));
-        TG_CUDA(ctx, cudaMemcpyAsync(h, d_ctl + 64, 8 * p * p, cudaMemcpyDeviceToHost, ctx->stream));
-        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        std::vector<u64> recv_cnt(p), recv_off(p + 1, 0);
-        for (int r = 0; r < p; ++r) { recv_cnt[r] = h[(size_t)r * p + me]; recv_off[r + 1] = recv_off[r] + recv_cnt[r]; }
-        ulonglong2* d_recv;
-        TG_TRY(tg_ws_get(ctx, WS_XCHG_RECV, (recv_off[p] + 2) * 16, (void**)&d_recv));
-        const int xprof_ = ctx->profile ? tg_prof_begin(ctx, TG_K_EXCHANGE) : -1;
-        TG_NCCL(ctx, ncclGroupStart());
-        for (int r = 0; r < p; ++r) {
-            if (send_cnt[r]) TG_NCCL(ctx, ncclSend((const ulonglong2*)d_send + send_off[r], send_cnt[r] * 16, ncclUint8, r, ctx->comm, ctx->stream));
-            if (recv_cnt[r]) TG_NCCL(ctx, ncclRecv(d_recv + recv_off[r], recv_cnt[r] * 16, ncclUint8, r, ctx->comm, ctx->stream));
-        }
-        TG_NCCL(ctx, ncclGroupEnd());
-        if (xprof_ >= 0) tg_prof_end(ctx, xprof_);
-        d_post_in = d_recv;
-        m_post = recv_off[p];
-    }
+    // partition by Hash128to64(0,key) % p and exchange (replaces the MixStream writers, :109-114): one pass that stores every
+    // partial aggregate into its owner's exchange window
+    HashDigit fn = { (u32)p };
+    XchgResult xr;
+    TG_TRY((exchange_scatter<2, HashDigit>(ctx, d_pre, m, fn, &xr)));
+    const void* d_post_in = xr.d_recv;
+    const u64 m_post = xr.n_recv;
     // post phase (ReduceByHashPostPhase, ProcessChannel + PushData: api/reduce_by_key.hpp:176-211)
     void* d_out;
     TG_TRY(tg_ws_get(ctx, WS_OUT, (m_post + 2) * 16, &d_out));      // (the pre phase's output was consumed by the partition)
@@ -720,42 +693,16 @@ int tg_reduce_to_index(tg_ctx* ctx, const tg_kv_desc* desc, const void* d_in, si
     const void* d_post = d_pre;
     u64 m_post = m;
     if (p > 1) {
-        if (m >= (1u << 30)) return tg_set_error(ctx, TG_ERR_TOO_LARGE, "reduce_to_index: %llu partial aggregates", (unsigned long long)m);
-        void* d_send;
-        TG_TRY(tg_ws_get(ctx, WS_XCHG_SEND, (m + 2) * 16, &d_send));
         RangeDigit fn = { result_size, (u32)p };
-        u32* d_counts = nullptr;
-        TG_TRY((partition_chunked<2, RangeDigit>(ctx, d_pre, d_send, m, fn, &d_counts, nullptr)));
-        u32* hc = (u32*)ctx->pinned;
-        TG_CUDA(ctx, cudaMemcpyAsync(hc, d_counts, RADIX * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        std::vector<u64> send_cnt(p), send_off(p + 1, 0);
-        for (int r = 0; r < p; ++r) { send_cnt[r] = hc[r]; send_off[r + 1] = send_off[r] + send_cnt[r]; }
-        u64* h = (u64*)ctx->pinned;
-        u64* d_ctl;
-        TG_TRY(tg_ws_get(ctx, WS_MISC, 1 << 16, (void**)&d_ctl));
-        for (int r = 0; r < p; ++r) h[r] = send_cnt[r];
-        TG_CUDA(ctx, cudaMemcpyAsync(d_ctl, h, 8 * p, cudaMemcpyHostToDevice, ctx->stream));
-        TG_NCCL(ctx, ncclAllGather(d_ctl, d_ctl + 64, p, ncclUint64, ctx->comm, ctx->stream));
-        TG_CUDA(ctx, cudaMemcpyAsync(h, d_ctl + 64, 8 * p * p, cudaMemcpyDeviceToHost, ctx->stream));
-        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        std::vector<u64> recv_cnt(p), recv_off(p + 1, 0);
-        for (int r = 0; r < p; ++r) { recv_cnt[r] = h[(size_t)r * p + me]; recv_off[r + 1] = recv_off[r] + recv_cnt[r]; }
-        ulonglong2* d_recv;
-        TG_TRY(tg_ws_get(ctx, WS_XCHG_RECV, (recv_off[p] + 2) * 16, (void**)&d_recv));
-        const int xprof_ = ctx->profile ? tg_prof_begin(ctx, TG_K_EXCHANGE) : -1;
-        TG_NCCL(ctx, ncclGroupStart());
-        for (int r = 0; r < p; ++r) {
-            if (send_cnt[r]) TG_NCCL(ctx, ncclSend((const ulonglong2*)d_send + send_off[r], send_cnt[r] * 16, ncclUint8, r, ctx->comm, ctx->stream));
-            if (recv_cnt[r]) TG_NCCL(ctx, ncclRecv(d_recv + recv_off[r], recv_cnt[r] * 16, ncclUint8, r, ctx->comm, ctx->stream));
-        }
-        TG_NCCL(ctx, ncclGroupEnd());
-        if (xprof_ >= 0) tg_prof_end(ctx, xprof_);
+        XchgResult xr;
+        TG_TRY((exchange_scatter<2, RangeDigit>(ctx, d_pre, m, fn, &xr)));
+        const ulonglong2* d_recv = (const ulonglong2*)xr.d_recv;
+        const u64 n_recv = xr.n_recv;
         // post phase, first half: one item per index
         void* d_agg;
-        TG_TRY(tg_ws_get(ctx, WS_OUT, (recv_off[p] + 2) * 16, &d_agg));
+        TG_TRY(tg_ws_get(ctx, WS_OUT, (n_recv + 2) * 16, &d_agg));
         u64 distinct = 0;
-        TG_TRY(run_partitioned_aggregate(ctx, op, d_recv, recv_off[p], d_agg, &distinct));
+        TG_TRY(run_partitioned_aggregate(ctx, op, d_recv, n_recv, d_agg, &distinct));
         d_post = d_agg;
         m_post = distinct;
     }

@@ -21,6 +21,7 @@
 #include "tg_partition.cuh"
 #include "tg_keys.cuh"
 #include "tg_segmented.cuh"
+#include "tg_exchange.cuh"
 
 using namespace tgp;
 
@@ -36,7 +37,9 @@ struct SplitterDigit {
     u32 nspl;
     u64 gbase;
     KeyView kv;
+    const u64* gbase_dev;          // if set: the worker's global index base, written by select_splitters_kernel
     static constexpr bool kStoreDigit = true;
+    __device__ __forceinline__ void init() { if (gbase_dev) gbase = *gbase_dev; }
     template <class Item>
     __device__ __forceinline__ u32 operator()(const Item& v, u32 pos) const {
         Canon k = canon_key(v, kv);
@@ -64,6 +67,93 @@ __global__ void draw_samples_kernel(const typename ItemT<WORDS>::type* __restric
     Canon c = canon_key(v, kv);
     CanonIdx ci = { c.hi, c.lo, gbase + index };
     out_canon[i] = ci;
+}
+
+// ---- the sample of a worker, drawn and ordered on the device -------------------------------------------------------
+// One slot per worker travels in the sample all-gather: a header and up to SAMPLE_MAX (key, LOCAL index) pairs in
+// LessSampleIndex order (api/sort.hpp:419-422; the global index base is added by the reader, which knows every n_local).
+constexpr u32 SAMPLE_MAX = 3008;             // >= tg_sample_size(2^30 - 1) = 2999
+struct SampleHdr { u64 n_local, ns, pad0, pad1; };
+constexpr size_t SAMPLE_SLOT_BYTES = sizeof(SampleHdr) + (size_t)SAMPLE_MAX * sizeof(CanonIdx);
+constexpr int SRANK_THREADS = 1024;
+
+// every CTA gathers all ns samples (items at positions rng % n: OnPreOpFile's reservoir stand-in, api/sort.hpp:162-170)
+// into shared memory; warp w of CTA b ranks samples b*32+w, +grid*32, ... by counting (ties of identical pairs by draw
+// order) and stores each at its rank
+template <int WORDS>
+__global__ void __launch_bounds__(SRANK_THREADS)
+sample_rank_kernel(const typename ItemT<WORDS>::type* __restrict__ in, u64 n, u64 seed, u32 ns, KeyView kv,
+                   unsigned char* __restrict__ slot) {
+    extern __shared__ __align__(16) unsigned char srank_smem[];
+    CanonIdx* const sm = reinterpret_cast<CanonIdx*>(srank_smem);
+    for (u32 i = threadIdx.x; i < ns; i += SRANK_THREADS) {
+        const u64 index = splitmix64_dev(seed + i) % n;
+        const Canon c = canon_key(in[index], kv);
+        sm[i] = CanonIdx{ c.hi, c.lo, index };
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<SampleHdr*>(slot) = SampleHdr{ n, ns, 0, 0 };
+    __syncthreads();
+    CanonIdx* const out = reinterpret_cast<CanonIdx*>(slot + sizeof(SampleHdr));
+    const u32 lane = lane_id(), warp = threadIdx.x >> 5;
+    for (u32 j = blockIdx.x * (SRANK_THREADS / 32) + warp; j < ns; j += gridDim.x * (SRANK_THREADS / 32)) {
+        const CanonIdx me = sm[j];
+        u32 cnt = 0;
+        for (u32 x = lane; x < ns; x += 32) {
+            const CanonIdx o = sm[x];
+            const bool eq = o.hi == me.hi && o.lo == me.lo && o.idx == me.idx;
+            cnt += (canonidx_less(o, me) || (eq && x < j)) ? 1u : 0u;
+        }
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (lane == 0) out[cnt] = me;
+    }
+}
+
+// Splitters from the p gathered, ordered samples (FindAndSendSplitters, api/sort.hpp:337-378): sample (q, j) has global
+// rank j + sum over the other workers of the number of their samples below it (global indices of different workers are
+// disjoint: no ties across lists); the sample whose rank is floor(i * S / p) is splitter i.  Every rank runs this on the
+// same bytes and gets the same splitters.  ctl[0] = this worker's global index base, ctl[1] = total items, ctl[2] = S.
+__global__ void __launch_bounds__(256)
+select_splitters_kernel(const unsigned char* __restrict__ slots, int p, int me, CanonIdx* __restrict__ spl, u64* __restrict__ ctl) {
+    __shared__ u64 prefix[TG_MAX_RANKS + 1];
+    __shared__ u32 ns_of[TG_MAX_RANKS];
+    __shared__ u64 total_s;
+    if (threadIdx.x == 0) {
+        u64 acc = 0, S = 0;
+        for (int q = 0; q < p; ++q) {
+            const SampleHdr h = *reinterpret_cast<const SampleHdr*>(slots + (size_t)q * SAMPLE_SLOT_BYTES);
+            prefix[q] = acc;
+            acc += h.n_local;
+            ns_of[q] = (u32)h.ns;
+            S += h.ns;
+        }
+        prefix[p] = acc;
+        total_s = S;
+        if (blockIdx.x == 0) { ctl[0] = prefix[me]; ctl[1] = acc; ctl[2] = S; }
+    }
+    __syncthreads();
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = (int)(t / SAMPLE_MAX);
+    const u32 j = t % SAMPLE_MAX;
+    if (q >= p || j >= ns_of[q]) return;
+    auto list = [&](int w) { return reinterpret_cast<const CanonIdx*>(slots + (size_t)w * SAMPLE_SLOT_BYTES + sizeof(SampleHdr)); };
+    CanonIdx mine = list(q)[j];
+    mine.idx += prefix[q];
+    u64 rank = j;
+    for (int w = 0; w < p; ++w) {
+        if (w == q) continue;
+        const CanonIdx* l = list(w);
+        u32 lo = 0, hi = ns_of[w];
+        while (lo < hi) {
+            const u32 mid = (lo + hi) >> 1;
+            CanonIdx o = l[mid];
+            o.idx += prefix[w];
+            if (canonidx_less(o, mine)) lo = mid + 1; else hi = mid;
+        }
+        rank += lo;
+    }
+    const double splitting_size = (double)total_s / (double)p;
+    for (int i = 1; i < p; ++i)
+        if ((u64)((double)i * splitting_size) == rank) spl[i - 1] = mine;
 }
 
 // ---- number of local items equal to splitter j's key with global index <= splitter j's index ------------
@@ -261,6 +351,57 @@ void pick_splitters(std::vector<CanonIdx>& samples, uint32_t p, std::vector<Cano
     for (size_t q : want) spl->push_back(samples[q]);
 }
 
+// samples of every worker and the splitters, all on the device (no host round trip): d_spl[p-1] in LessSampleIndex order,
+// d_ctl = { this worker's global index base, total items, total samples, status flags }.  `items` are WORDS-word items whose
+// canonical key is described by kv.  Collective (one ncclAllGather).
+template <int WORDS>
+int device_splitters(tg_ctx* ctx, const KeyView& kv, const void* d_items, size_t n_local, uint64_t rng_seed, bool too_large,
+                     CanonIdx** d_spl_out, u64** d_ctl_out) {
+    typedef typename ItemT<WORDS>::type Item;
+    const int p = ctx->nranks, me = ctx->rank;
+    unsigned char* d_samp;      // [p] gathered slots | my slot | splitters | ctl
+    TG_TRY(tg_ws_get(ctx, WS_SAMPLES, (size_t)(p + 1) * SAMPLE_SLOT_BYTES + 4096, (void**)&d_samp));
+    unsigned char* d_mine = d_samp + (size_t)p * SAMPLE_SLOT_BYTES;
+    CanonIdx* d_spl = reinterpret_cast<CanonIdx*>(d_mine + SAMPLE_SLOT_BYTES);
+    u64* d_ctl = reinterpret_cast<u64*>(d_spl + TG_MAX_RANKS);
+    const u64 n_eff = too_large ? 0 : n_local;
+    const u64 want = n_eff ? tg_sample_size(n_eff) : 0;
+    const u32 ns = (u32)(want < n_eff ? want : n_eff);
+    if (ns) {
+        auto kern = sample_rank_kernel<WORDS>;
+        const size_t smem = (size_t)ns * sizeof(CanonIdx);
+        if (ctx->kernel_cfg.find((const void*)kern) == ctx->kernel_cfg.end()) {
+            TG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SAMPLE_MAX * sizeof(CanonIdx))));
+            ctx->kernel_cfg[(const void*)kern] = 1;
+        }
+        const int grid = (int)((ns + 31) / 32) < ctx->sm_count ? (int)((ns + 31) / 32) : ctx->sm_count;
+        TG_LAUNCH(ctx, kern, grid, SRANK_THREADS, smem, (const Item*)d_items, (u64)n_eff,
+                  rng_seed * 0x9E3779B97F4A7C15ull + (u64)me * 0x100000000ull, ns, kv, d_mine);
+    }
+    else {
+        SampleHdr* h = (SampleHdr*)((u64*)ctx->pinned + 2560);        // (pinned scratch, byte offset 20 KB)
+        *h = SampleHdr{ 0, 0, too_large ? 1ull : 0ull, 0 };
+        TG_CUDA(ctx, cudaMemcpyAsync(d_mine, h, sizeof(SampleHdr), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    TG_NCCL(ctx, ncclAllGather(d_mine, d_samp, SAMPLE_SLOT_BYTES, ncclUint8, ctx->comm, ctx->stream));
+    TG_LAUNCH(ctx, select_splitters_kernel, (p * SAMPLE_MAX + 255) / 256, 256, 0, (const unsigned char*)d_samp, p, me, d_spl, d_ctl);
+    *d_spl_out = d_spl;
+    *d_ctl_out = d_ctl;
+    return TG_OK;
+}
+
+// an operator input that lies inside the exchange window (the previous collective operator's result) is moved out of
+// the peers' way first
+int evacuate_window_input(tg_ctx* ctx, void** d_in, size_t bytes) {
+    const char* b = (const char*)ctx->xwin.base;
+    if (!b || (const char*)*d_in < b || (const char*)*d_in >= b + ctx->xwin.cap) return TG_OK;
+    void* d;
+    TG_TRY(tg_ws_get(ctx, WS_IN, bytes + 16, &d));
+    if (d != *d_in) TG_CUDA(ctx, cudaMemcpyAsync(d, *d_in, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    *d_in = d;
+    return TG_OK;
+}
+
 template <int WORDS>
 int sort_multi_impl(tg_ctx* ctx, const tg_key_desc* desc, const KeyView& kv, void* d_in, size_t n_local,
                     uint64_t rng_seed, void** out_dptr, size_t* out_n) {
@@ -268,95 +409,61 @@ int sort_multi_impl(tg_ctx* ctx, const tg_key_desc* desc, const KeyView& kv, voi
     const int p = ctx->nranks, me = ctx->rank;
     const size_t s = sizeof(Item);
     u64* h = (u64*)ctx->pinned;                      // host scratch (pinned, 1 MiB)
-    u64* d_ctl;                                      // device control-plane scratch
-    TG_TRY(tg_ws_get(ctx, WS_MISC, 1 << 16, (void**)&d_ctl));
+    const bool too_large = n_local >= (1u << 30);    // reported to every rank through the sample header: a uniform error
+    TG_TRY(evacuate_window_input(ctx, &d_in, n_local * s));
 
-    // (1) ExPrefixSumTotal(local_items_) (api/sort.hpp:541): all-gather the shard sizes
-    h[0] = n_local;
-    TG_CUDA(ctx, cudaMemcpyAsync(d_ctl, h, 8, cudaMemcpyHostToDevice, ctx->stream));
-    TG_NCCL(ctx, ncclAllGather(d_ctl, d_ctl + 8, 1, ncclUint64, ctx->comm, ctx->stream));
-    TG_CUDA(ctx, cudaMemcpyAsync(h, d_ctl + 8, 8 * p, cudaMemcpyDeviceToHost, ctx->stream));
-    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    std::vector<u64> n_of(p);
-    u64 total = 0, prefix = 0;
-    for (int r = 0; r < p; ++r) { n_of[r] = h[r]; if (r < me) prefix += h[r]; total += h[r]; }
-    if (total == 0) { *out_dptr = nullptr; *out_n = 0; return TG_OK; }        // :550-559
-    if (n_local >= (1u << 30)) return tg_set_error(ctx, TG_ERR_TOO_LARGE, "sort: n_local=%zu", n_local);
-
-    // (2) samples: min(n, floor(log2(n)*100)) per worker (:151-175), all-gathered instead of sent to worker 0
-    std::vector<u32> ns_of(p);
-    u32 max_s = 1;
-    for (int r = 0; r < p; ++r) {
-        u64 want = n_of[r] ? tg_sample_size(n_of[r]) : 0;
-        ns_of[r] = (u32)(want < n_of[r] ? want : n_of[r]);
-        if (ns_of[r] > max_s) max_s = ns_of[r];
-    }
-    CanonIdx* d_samp;
-    TG_TRY(tg_ws_get(ctx, WS_SAMPLES, (size_t)(p + 1) * max_s * sizeof(CanonIdx) + 4096, (void**)&d_samp));
-    CanonIdx* d_mine = d_samp + (size_t)p * max_s;
-    if (ns_of[me])
-        TG_LAUNCH(ctx, draw_samples_kernel<WORDS>, (ns_of[me] + 255) / 256, 256, 0, (const Item*)d_in, (u64)n_local, prefix,
-                  rng_seed * 0x9E3779B97F4A7C15ull + (u64)me * 0x100000000ull, ns_of[me], kv, (Item*)nullptr, d_mine);
-    TG_NCCL(ctx, ncclAllGather(d_mine, d_samp, (size_t)max_s * sizeof(CanonIdx), ncclUint8, ctx->comm, ctx->stream));
-    std::vector<CanonIdx> all((size_t)p * max_s);
-    TG_CUDA(ctx, cudaMemcpyAsync(all.data(), d_samp, all.size() * sizeof(CanonIdx), cudaMemcpyDeviceToHost, ctx->stream));
-    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    std::vector<CanonIdx> samples, spl;
-    for (int r = 0; r < p; ++r)
-        for (u32 i = 0; i < ns_of[r]; ++i) samples.push_back(all[(size_t)r * max_s + i]);
-    pick_splitters(samples, (uint32_t)p, &spl);      // identical on every rank (same data, same order)
-    const u32 nspl = (u32)spl.size();
+    // (1) + (2) ExPrefixSumTotal(local_items_) (api/sort.hpp:541), samples (:151-175) and FindAndSendSplitters (:337-378):
+    // one all-gather, splitters selected on the device by every rank
+    CanonIdx* d_spl;
+    u64* d_ctl;
+    TG_TRY((device_splitters<WORDS>(ctx, kv, d_in, n_local, rng_seed, too_large, &d_spl, &d_ctl)));
+    const u32 nspl = (u32)(p - 1);
+    u64* h_ctl = h + 3072;                           // byte offset 24 KB: ctl[4] | splitters
+    CanonIdx* h_spl = (CanonIdx*)(h_ctl + 4);
+    TG_CUDA(ctx, cudaMemcpyAsync(h_ctl, d_ctl, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    TG_CUDA(ctx, cudaMemcpyAsync(h_spl, d_spl, nspl * sizeof(CanonIdx), cudaMemcpyDeviceToHost, ctx->stream));
 
     if (classify_first()) {
-        // The reference's own order (api/sort.hpp:615-742): classify + scatter by the splitters (TransmitItems), exchange, then
-        // sort what was received.  One partition pass and one local sort instead of a local sort and ceil(log2 p) merge levels.
-        CanonIdx* d_splc = d_samp;
-        TG_CUDA(ctx, cudaMemcpyAsync(d_splc, spl.data(), nspl * sizeof(CanonIdx), cudaMemcpyHostToDevice, ctx->stream));
-        SplitterDigit fn = { d_splc, nspl, prefix, kv };
-        void* d_part;
-        TG_TRY(tg_ws_get(ctx, WS_XCHG_SEND, (n_local + 1) * s, &d_part));
-        u32 *d_tot = nullptr, *d_gb = nullptr;
-        TG_TRY((partition_chunked<WORDS, SplitterDigit>(ctx, d_in, d_part, n_local, fn, &d_tot, &d_gb)));
-        u32* hc = (u32*)ctx->pinned;
-        TG_CUDA(ctx, cudaMemcpyAsync(hc, d_tot, RADIX * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        std::vector<u64> send_cnt(p), send_off(p + 1, 0);
-        for (int r = 0; r < p; ++r) { send_cnt[r] = hc[r]; send_off[r + 1] = send_off[r] + send_cnt[r]; }
-        for (int r = 0; r < p; ++r) h[r] = send_cnt[r];
-        TG_CUDA(ctx, cudaMemcpyAsync(d_ctl, h, 8 * p, cudaMemcpyHostToDevice, ctx->stream));
-        TG_NCCL(ctx, ncclAllGather(d_ctl, d_ctl + 64, p, ncclUint64, ctx->comm, ctx->stream));
-        TG_CUDA(ctx, cudaMemcpyAsync(h, d_ctl + 64, 8 * p * p, cudaMemcpyDeviceToHost, ctx->stream));
-        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        std::vector<u64> recv_cnt(p), recv_off(p + 1, 0);
-        for (int r = 0; r < p; ++r) { recv_cnt[r] = h[(size_t)r * p + me]; recv_off[r + 1] = recv_off[r] + recv_cnt[r]; }
-        const u64 n_recv = recv_off[p];
-        if (n_recv >= (1u << 30)) return tg_set_error(ctx, TG_ERR_TOO_LARGE, "sort: %llu items received", (unsigned long long)n_recv);
-        Item* d_recv;
-        TG_TRY(tg_ws_get(ctx, WS_XCHG_RECV, (n_recv + 2) * s, (void**)&d_recv));
-        const int xprof_ = ctx->profile ? tg_prof_begin(ctx, TG_K_EXCHANGE) : -1;
-        TG_NCCL(ctx, ncclGroupStart());
-        for (int r = 0; r < p; ++r) {
-            if (send_cnt[r]) TG_NCCL(ctx, ncclSend((const Item*)d_part + send_off[r], send_cnt[r] * s, ncclUint8, r, ctx->comm, ctx->stream));
-            if (recv_cnt[r]) TG_NCCL(ctx, ncclRecv(d_recv + recv_off[r], recv_cnt[r] * s, ncclUint8, r, ctx->comm, ctx->stream));
-        }
-        TG_NCCL(ctx, ncclGroupEnd());
-        if (xprof_ >= 0) tg_prof_end(ctx, xprof_);
+        // The reference's own order (api/sort.hpp:615-742): classify + scatter by the splitters (TransmitItems) and the exchange
+        // — here one kernel that stores every item into its destination worker's window — then sort what was received.
+        SplitterDigit fn = { d_spl, nspl, 0, kv, d_ctl };
+        XchgResult xr;
+        TG_TRY((exchange_scatter<WORDS, SplitterDigit>(ctx, d_in, too_large ? 0 : n_local, fn, &xr)));      // (synchronises once)
+        if (h_ctl[3]) return tg_set_error(ctx, TG_ERR_TOO_LARGE, "sort: a worker holds 2^30 or more items");
+        if (h_ctl[1] == 0) { *out_dptr = nullptr; *out_n = 0; return TG_OK; }                           // :550-559
         // ReceiveItems + SortAndWriteToFile (:665-742): the received items arrive grouped by source worker in worker order, each
         // group in input order: the stable local sort leaves equal keys in global input order
+        const u64 n_recv = xr.n_recv;
         void* d_tmp2;
         TG_TRY(tg_ws_get(ctx, WS_SORT_TMP, (n_recv + 2) * s, &d_tmp2));
-        void* d_res = d_recv;
-        TG_TRY(tg_radix_sort_items(ctx, desc, d_recv, d_tmp2, n_recv, &d_res));
+        // this worker's keys lie between its two splitters: the most significant bit in which they can differ
+        const int saved_top = ctx->spec_top_bit;
+        if (kv.kind == TG_KEY_UINT_LE && !kv.desc && kv.bytes == 8 && (kv.off & 7) == 0 && h_ctl[2] > 0) {
+            const u64 lo = me > 0 ? h_spl[me - 1].lo : 0ull, hi = me < p - 1 ? h_spl[me].lo : ~0ull;
+            const u64 x = lo ^ hi;
+            ctx->spec_top_bit = x ? 64 - __builtin_clzll(x) : 8;
+        }
+        void* d_res = xr.d_recv;
+        const int st = tg_radix_sort_items(ctx, desc, xr.d_recv, d_tmp2, n_recv, &d_res);
+        ctx->spec_top_bit = saved_top;
+        TG_TRY(st);
         *out_dptr = d_res;
         *out_n = (size_t)n_recv;
         return TG_OK;
     }
 
+    // ---- TG_SORT_PIPELINE=merge (tests only): sorted runs -> boundaries -> NCCL Alltoallv -> merge of the received runs
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h_ctl[3]) return tg_set_error(ctx, TG_ERR_TOO_LARGE, "sort: a worker holds 2^30 or more items");
+    if (h_ctl[1] == 0) { *out_dptr = nullptr; *out_n = 0; return TG_OK; }
+    const u64 prefix = h_ctl[0];
+    u64* d_ctl2;                                     // device control-plane scratch
+    TG_TRY(tg_ws_get(ctx, WS_MISC, 1 << 16, (void**)&d_ctl2));
+    u64* d_ctl_old = d_ctl; (void)d_ctl_old;
+    d_ctl = d_ctl2;
     // (3) per-splitter tie counts on the unsorted shard, (4) local radix sort, (5) bucket boundaries
-    CanonIdx* d_spl = d_samp;       // reuse
     u32* d_tie = (u32*)(d_ctl + 1024);
     u64* d_bnd = d_ctl + 2048;
-    TG_CUDA(ctx, cudaMemcpyAsync(d_spl, spl.data(), nspl * sizeof(CanonIdx), cudaMemcpyHostToDevice, ctx->stream));
     TG_CUDA(ctx, cudaMemsetAsync(d_tie, 0, 4096, ctx->stream));
     if (n_local && nspl)
         TG_LAUNCH(ctx, tie_count_kernel<WORDS>, ctx->sm_count * 4, 512, 0, (const Item*)d_in, (u32)n_local, prefix, kv, d_spl, nspl, d_tie);
@@ -641,7 +748,7 @@ int tg_classify_scatter(tg_ctx* ctx, const tg_key_desc* desc, const void* d_in, 
     CanonIdx* d_spl;
     TG_TRY(tg_ws_get(ctx, WS_SAMPLES, (size_t)p * sizeof(CanonIdx) + 256, (void**)&d_spl));
     if (p > 1) TG_CUDA(ctx, cudaMemcpyAsync(d_spl, spl.data(), (p - 1) * sizeof(CanonIdx), cudaMemcpyHostToDevice, ctx->stream));
-    SplitterDigit fn = { d_spl, p - 1, global_index_base, kv };
+    SplitterDigit fn = { d_spl, p - 1, global_index_base, kv, nullptr };
     u32* d_counts = nullptr;
     if (desc->item_bytes == 8) TG_TRY((partition_chunked<1, SplitterDigit>(ctx, d_in, d_out, n, fn, &d_counts, nullptr)));
     else TG_TRY((partition_chunked<2, SplitterDigit>(ctx, d_in, d_out, n, fn, &d_counts, nullptr)));

@@ -29,9 +29,11 @@ struct DigitList {
 // (orand[2w] = OR, orand[2w+1] = AND of word w; tells which digit positions are constant over the whole input).
 template <int WORDS, class DigitFn, bool ORAND>
 __global__ void __launch_bounds__(512) chunk_hist_kernel(const typename ItemT<WORDS>::type* __restrict__ in, u32 n, u32 chunk_items,
-                                                         const DigitFn fn, u32* __restrict__ chunkcount /* [grid][RADIX] */,
+                                                         const DigitFn fn_param, u32* __restrict__ chunkcount /* [grid][RADIX] */,
                                                          u64* __restrict__ orand) {
     typedef typename ItemT<WORDS>::type Item;
+    DigitFn fn = fn_param;
+    fn.init();
     constexpr int U = 4;
     __shared__ u32 sh[RADIX];
     for (int i = threadIdx.x; i < RADIX; i += blockDim.x) sh[i] = 0;
@@ -122,8 +124,11 @@ static __global__ void __launch_bounds__(4 * RADIX) chunk_scan_kernel(const u32*
 // segment does not change while passes permute the items inside the segment: one read serves all of them).
 template <int WORDS, class DigitFn, int NPOS>
 __global__ void __launch_bounds__(512) seg_count_kernel(const typename ItemT<WORDS>::type* __restrict__ in, SegList sl,
-                                                        const DigitList<DigitFn> dl, u32* __restrict__ segcount /* [seg][NPOS][RADIX] */) {
+                                                        const DigitList<DigitFn> dl_param, u32* __restrict__ segcount /* [seg][NPOS][RADIX] */) {
     typedef typename ItemT<WORDS>::type Item;
+    DigitList<DigitFn> dl = dl_param;
+#pragma unroll
+    for (int p = 0; p < NPOS; ++p) dl.fn[p].init();
     __shared__ u32 sh[NPOS * RADIX];
     constexpr int U = 4;
     for (u32 j = blockIdx.x; j < sl.num_tiles; j += gridDim.x) {
