@@ -110,6 +110,8 @@ enum { TG_K_RADIX_HIST = 0, TG_K_PARTITION = 1, TG_K_MERGE = 2, TG_K_PREAGG = 3,
        TG_K_EXCHANGE = 9 /* the NCCL Alltoallv (not a kernel of ours: timed like one) */, TG_K_NUM = 10 };
 int tg_profile_enable(tg_ctx* ctx, int on);
 int tg_profile_get(tg_ctx* ctx, int kernel_class, float* out_total_ms, uint64_t* out_launches);
+/* the individual launch durations of `kernel_class` in launch order (up to `capacity`); *out_n = how many there are */
+int tg_profile_list(tg_ctx* ctx, int kernel_class, float* out_ms, size_t capacity, size_t* out_n);
 /* page-locked host memory (what the BlockPool arenas should be for full PCIe bandwidth; the host shim
  * can equally cudaHostRegister its existing ByteBlocks) */
 int tg_host_alloc(tg_ctx* ctx, size_t bytes, void** out_hptr);

@@ -24,3 +24,15 @@ def test_collective_operators_on_n_gpus(world, pipeline):
     env = dict(os.environ, TG_SORT_PIPELINE=pipeline)
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert res.returncode == 0 and "MULTI_GPU_PARITY_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-5000:]
+
+
+def test_collective_operators_nccl_exchange():
+    """TG_EXCHANGE=nccl: the two-step exchange (local partition, grouped ncclSend/ncclRecv) that is used where peers cannot map
+    each other's windows"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29631", os.path.join(HERE, "multi_gpu_worker.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, TG_EXCHANGE="nccl"))
+    assert res.returncode == 0 and "MULTI_GPU_PARITY_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-5000:]

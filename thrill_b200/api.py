@@ -48,6 +48,25 @@ First = _Functor("first", capi.OP_FIRST)
 KeyIsFirst = _Functor("pair.first")                       # the key extractor ReducePair builds (:444-449)
 
 
+def bind_to_gpu_numa_node(device):
+    """Run this worker process on the CPUs next to its GPU (nvidia-smi topo -m "CPU Affinity"): the pinned staging
+    buffers it allocates afterwards, and the copies it issues, stay on the GPU's NUMA node.  What a Thrill launcher does
+    with numactl per worker; without it eight workers share one node's memory controllers for their PCIe traffic."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device)
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {i for i in range(ncpu) if (mask[i // 64] >> (i % 64)) & 1} & os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception:          # noqa: BLE001  (no NVML, no permission: run unbound)
+        pass
+    return None
+
+
 class Context(object):
     """One worker = one GPU (api/context.hpp:243-245)."""
 
@@ -65,6 +84,8 @@ class Context(object):
         world = int(os.environ.get("WORLD_SIZE", "1"))
         local = int(os.environ.get("LOCAL_RANK", str(rank)))
         uid = None
+        if world > 1 and os.environ.get("TG_NUMA_BIND", "1") != "0":
+            bind_to_gpu_numa_node(local)
         if world > 1:
             import torch.distributed as dist
             if not dist.is_initialized():

@@ -67,6 +67,7 @@ SYMBOLS = [
     ("tg_prefix_sort_fallbacks", _u64, [_vp]),
     ("tg_profile_enable", _i, [_vp, _i]),
     ("tg_profile_get", _i, [_vp, _i, _P(C.c_float), _P(_u64)]),
+    ("tg_profile_list", _i, [_vp, _i, _P(C.c_float), _sz, _P(_sz)]),
     ("tg_host_alloc", _i, [_vp, _sz, _P(_vp)]),
     ("tg_host_free", _i, [_vp, _vp]),
     ("tg_upload", _i, [_vp, _vp, _vp, _sz]),
@@ -224,6 +225,11 @@ class Ctx(object):
         ms = C.c_float(); cnt = C.c_uint64()
         self.ck(self.L.tg_profile_get(self.h, cls, C.byref(ms), C.byref(cnt)))
         return ms.value, cnt.value
+
+    def profile_list(self, cls, cap=4096):
+        buf = (C.c_float * cap)(); n = C.c_size_t()
+        self.ck(self.L.tg_profile_list(self.h, cls, buf, cap, C.byref(n)))
+        return [buf[i] for i in range(min(n.value, cap))]
 
     def host_alloc(self, nbytes):
         """page-locked host buffer as a numpy uint8 array (freed with host_free)"""

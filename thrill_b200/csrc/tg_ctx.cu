@@ -94,6 +94,20 @@ int tg_profile_get(tg_ctx* ctx, int kernel_class, float* out_total_ms, uint64_t*
     return TG_OK;
 }
 
+int tg_profile_list(tg_ctx* ctx, int kernel_class, float* out_ms, size_t capacity, size_t* out_n) {
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    size_t cnt = 0;
+    for (auto& e : ctx->prof_events)
+        if (e.cls == kernel_class) {
+            float ms = 0.f;
+            TG_CUDA(ctx, cudaEventElapsedTime(&ms, e.a, e.b));
+            if (out_ms && cnt < capacity) out_ms[cnt] = ms;
+            ++cnt;
+        }
+    if (out_n) *out_n = cnt;
+    return TG_OK;
+}
+
 int tg_host_alloc(tg_ctx* ctx, size_t bytes, void** out_hptr) {
     if (!out_hptr) return TG_ERR_ARG;
     cudaError_t e = cudaMallocHost(out_hptr, bytes ? bytes : 16);
