@@ -74,6 +74,7 @@ typedef struct {
 
 /* ---- context ---------------------------------------------------------------------------------------- */
 int tg_version(void);
+int tg_device_count(void);                          /* sm_100 GPUs visible to this process (0: none, no CPU fallback) */
 const char* tg_strerror(int status);
 const char* tg_last_error(const tg_ctx* ctx);
 

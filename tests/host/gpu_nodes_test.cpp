@@ -40,6 +40,22 @@ static inline uint64_t splitmix64(uint64_t x) {
 
 static std::atomic<int> g_failures { 0 };
 
+//! TeraSort's item (examples/terasort/terasort.cpp:31-42): 10 key bytes compared lexicographically, 90 payload bytes
+struct Record {
+    uint8_t key[10];
+    uint8_t value[90];
+    bool operator < (const Record& b) const { return std::lexicographical_compare(key, key + 10, b.key, b.key + 10); }
+    bool operator == (const Record& b) const { return memcmp(this, &b, sizeof(Record)) == 0; }
+} TLX_ATTRIBUTE_PACKED;
+static_assert(sizeof(Record) == 100, "struct Record packing incorrect.");
+namespace thrill_gpu {
+template <>
+struct ByteKeyTraits<Record>{
+    static constexpr bool is_byte_key = true;
+    static constexpr uint32_t key_offset = 0, key_bytes = 10;
+};
+} // namespace thrill_gpu
+
 int main(int argc, char** argv) {
     size_t n = argc > 1 ? strtoull(argv[1], nullptr, 10) : 2000000;
     int rc = api::Run(
@@ -107,6 +123,53 @@ int main(int argc, char** argv) {
                 std::sort(gpu.begin(), gpu.end());
                 bool ok = cpu == gpu;
                 if (ctx.my_rank() == 0) printf("%s SortStable->ReducePair chain n=%zu\n", ok ? "PASS" : "FAIL", n);
+                if (!ok) g_failures++;
+            }
+            // ---- SortStable of pairs by key: identical to the stock SortStable (equal keys in global input order) ----
+            {
+                using Pair = std::pair<uint64_t, uint64_t>;
+                auto pairs = api::Generate(ctx, n, [](size_t i) { return Pair(splitmix64(i + 3) % 997, i); }).Cache().Keep(2);
+                std::vector<Pair> cpu = pairs.SortStable([](const Pair& a, const Pair& b) { return a.first < b.first; }).AllGather();
+                std::vector<Pair> gpu = thrill_gpu::SortStable(pairs, thrill_gpu::LessFirst()).AllGather();
+                bool ok = cpu == gpu && cpu.size() == n;
+                if (ctx.my_rank() == 0) printf("%s SortStable pairs n=%zu\n", ok ? "PASS" : "FAIL", n);
+                if (!ok) g_failures++;
+            }
+            // ---- ReduceByKey(key_extractor, reduce_function) front door with the recognised functor pair ----
+            {
+                using Pair = std::pair<uint64_t, uint64_t>;
+                auto pairs = api::Generate(ctx, n, [](size_t i) { return Pair(splitmix64(i + 11) % 4099, i % 17); }).Cache().Keep(2);
+                std::vector<Pair> cpu = pairs.ReduceByKey(
+                    [](const Pair& p) { return p.first; },
+                    [](const Pair& a, const Pair& b) { return Pair(a.first, a.second + b.second); }).AllGather();
+                std::vector<Pair> gpu = thrill_gpu::ReduceByKey(
+                    pairs, thrill_gpu::KeyFirst(), thrill_gpu::OnSecond<std::plus<uint64_t> >()).AllGather();
+                std::sort(cpu.begin(), cpu.end());
+                std::sort(gpu.begin(), gpu.end());
+                bool ok = cpu == gpu;
+                if (ctx.my_rank() == 0) printf("%s ReduceByKey(KeyFirst, OnSecond<plus>) n=%zu distinct=%zu\n", ok ? "PASS" : "FAIL", n, cpu.size());
+                if (!ok) g_failures++;
+            }
+            // ---- TeraSort: Sort of 100-byte Records by their 10-byte key (examples/terasort/terasort.cpp:186-200) ----
+            {
+                const size_t nr = n / 4;
+                auto recs = api::Generate(ctx, nr, [](size_t i) {
+                                              Record r;
+                                              uint64_t a = splitmix64(2 * i + 42), b = splitmix64(2 * i + 43);
+                                              memcpy(r.key, &a, 8);
+                                              memcpy(r.key + 8, &b, 2);
+                                              for (size_t j = 0; j < 90; ++j) r.value[j] = static_cast<uint8_t>((i * 131 + j * 7) & 0xff);
+                                              return r;
+                                          }).Cache().Keep(2);
+                common::StatsTimerStart t_cpu;
+                std::vector<Record> cpu = recs.Sort().AllGather();
+                t_cpu.Stop();
+                common::StatsTimerStart t_gpu;
+                std::vector<Record> gpu = thrill_gpu::Sort(recs).AllGather();
+                t_gpu.Stop();
+                bool ok = cpu == gpu && cpu.size() == nr;
+                if (ctx.my_rank() == 0)
+                    printf("%s TeraSort Records n=%zu cpu=%.3fs gpu=%.3fs\n", ok ? "PASS" : "FAIL", nr, t_cpu.SecondsDouble(), t_gpu.SecondsDouble());
                 if (!ok) g_failures++;
             }
         });

@@ -49,6 +49,7 @@ _vp, _u64, _sz, _i, _u32 = C.c_void_p, C.c_uint64, C.c_size_t, C.c_int, C.c_uint
 _P = C.POINTER
 SYMBOLS = [
     ("tg_version", _i, []),
+    ("tg_device_count", _i, []),
     ("tg_strerror", C.c_char_p, [_i]),
     ("tg_last_error", C.c_char_p, [_vp]),
     ("tg_get_unique_id", _i, [_vp]),

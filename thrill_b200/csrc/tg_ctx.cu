@@ -119,7 +119,18 @@ int tg_host_free(tg_ctx* ctx, void* hptr) {
     return TG_OK;
 }
 
-int tg_version(void) { return 100; }
+int tg_version(void) { return 200; }
+
+int tg_device_count(void) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < ndev; ++d) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, d) == cudaSuccess && prop.major == 10) ++ok;
+    }
+    return ok == ndev ? ndev : 0;
+}
 
 const char* tg_strerror(int status) {
     switch (status) {

@@ -29,9 +29,9 @@
 #include <thrill/data/file.hpp>
 
 #include <array>
+#include <cstdlib>
+#include <cstring>
 #include <functional>
-#include <map>
-#include <mutex>
 #include <type_traits>
 #include <utility>
 #include <vector>
@@ -50,16 +50,24 @@ inline void Check(tg_ctx* c, int status, const char* what) {
         die("thrill_gpu: " << what << " failed: " << tg_strerror(status) << ": " << tg_last_error(c));
 }
 
-//! one tg_ctx per worker, created on first use (collective: every worker must reach its first GPU node)
+//! One tg_ctx per worker THREAD, created on first use (collective: every worker must reach its first GPU node) and shut
+//! down when the thread ends.  api::Run starts every worker on a thread of its own (api/context.cpp:RunLoopbackThreads /
+//! RunBackendLoopback), so the ctx — stream, workspaces, exchange window, NCCL communicator — lives exactly as long as the
+//! job's Context does: a second api::Run in the same process gets fresh threads and a fresh ctx, never a stale one.  On a
+//! hit the cached ctx is checked against the Context (a re-used thread, api::RunLocalSameThread) and rebuilt if it differs.
+struct WorkerCtxHolder {
+    tg_ctx* c = nullptr;
+    const Context* owner = nullptr;
+    size_t rank = 0, nranks = 0;
+    void Reset() { if (c) tg_shutdown(c); c = nullptr; owner = nullptr; }
+    ~WorkerCtxHolder() { Reset(); }
+};
+
 inline tg_ctx * WorkerCtx(Context& ctx) {
-    static std::mutex mutex;
-    static std::map<Context*, tg_ctx*> table;
-    {
-        std::lock_guard<std::mutex> lock(mutex);
-        auto it = table.find(&ctx);
-        if (it != table.end()) return it->second;
-    }
-    static_assert(!thrill::common::g_self_verify || true, "");
+    static thread_local WorkerCtxHolder holder;
+    if (holder.c && holder.owner == &ctx && holder.rank == ctx.my_rank() && holder.nranks == ctx.num_workers())
+        return holder.c;
+    holder.Reset();
     die_unless(!thrill::common::g_self_verify);     // Debug builds prefix every item with a typecode
     using Id = std::array<char, 128>;
     Id id;
@@ -68,12 +76,25 @@ inline tg_ctx * WorkerCtx(Context& ctx) {
         if (ctx.my_rank() == 0) Check(nullptr, tg_get_unique_id(id.data()), "tg_get_unique_id");
         id = ctx.net.Broadcast(id, 0);
     }
+    // worker -> GPU: the worker's index on its host (api/context.hpp: local_worker_id).  The in-process test networks
+    // (THRILL_NET=mock/local with several "hosts") put every host's workers into this one process: there the global rank
+    // picks the GPU, and two workers are never given the same device (NCCL and the peer mapping both need distinct GPUs).
+    int ndev = tg_device_count();
+    if (ndev <= 0) die("thrill_gpu: no sm_100 GPU visible (there is no CPU fallback in the GPU nodes)");
+    size_t device = ctx.local_worker_id();
+    const char* net = getenv("THRILL_NET");
+    if (ctx.num_hosts() > 1 && net && (!strcmp(net, "mock") || !strcmp(net, "local"))) device = ctx.my_rank();
+    if (device >= static_cast<size_t>(ndev))
+        die("thrill_gpu: worker " << ctx.my_rank() << " needs GPU " << device << " but only " << ndev << " are visible "
+            "(run with THRILL_WORKERS_PER_HOST <= number of GPUs)");
     tg_ctx* c = nullptr;
-    int st = tg_init(static_cast<int>(ctx.local_worker_id()), static_cast<int>(ctx.my_rank()),
+    int st = tg_init(static_cast<int>(device), static_cast<int>(ctx.my_rank()),
                      static_cast<int>(ctx.num_workers()), id.data(), &c);
     Check(c, st, "tg_init");
-    std::lock_guard<std::mutex> lock(mutex);
-    table[&ctx] = c;
+    holder.c = c;
+    holder.owner = &ctx;
+    holder.rank = ctx.my_rank();
+    holder.nranks = ctx.num_workers();
     return c;
 }
 
@@ -83,6 +104,26 @@ inline tg_ctx * WorkerCtx(Context& ctx) {
 template <typename ValueType, typename Compare, typename Enable = void>
 struct SortDesc {
     static constexpr bool supported = false;
+};
+//! Items whose order is the lexicographic order of a run of key bytes (TeraSort's Record{uint8 key[10]; uint8 value[90]} with
+//! operator< = std::lexicographical_compare of the keys, examples/terasort/terasort.cpp:31-42): specialise for the item type
+//!   template <> struct thrill_gpu::ByteKeyTraits<Record> { static constexpr bool is_byte_key = true;
+//!                                                          static constexpr uint32_t key_offset = 0, key_bytes = 10; };
+//! and thrill_gpu::Sort(dia) / Sort(dia, std::less<Record>()) take the GPU path (key_bytes <= 12, sizeof(T) % 4 == 0).
+template <typename ValueType>
+struct ByteKeyTraits {
+    static constexpr bool is_byte_key = false;
+};
+template <typename ValueType>
+struct SortDesc<ValueType, std::less<ValueType>, typename std::enable_if<ByteKeyTraits<ValueType>::is_byte_key>::type>{
+    static_assert(sizeof(ValueType) % 4 == 0 && ByteKeyTraits<ValueType>::key_bytes <= 12 &&
+                  ByteKeyTraits<ValueType>::key_offset + ByteKeyTraits<ValueType>::key_bytes <= sizeof(ValueType),
+                  "byte-key records: sizeof % 4 == 0 and a key of at most 12 bytes inside the item");
+    static constexpr bool supported = true;
+    static tg_key_desc make() {
+        return tg_key_desc { static_cast<uint32_t>(sizeof(ValueType)), ByteKeyTraits<ValueType>::key_offset,
+                             ByteKeyTraits<ValueType>::key_bytes, TG_KEY_BYTES_BE, 0, 0 };
+    }
 };
 template <typename Compare>
 struct SortDesc<uint64_t, Compare, typename std::enable_if<
@@ -131,6 +172,19 @@ template <>
 struct ReduceDesc<uint64_t, MaxU64>{
     static constexpr bool supported = true;
     static constexpr uint32_t op = TG_OP_MAX_U64;
+};
+
+//! The functors thrill_gpu::ReduceByKey recognises (DIA::ReduceByKey takes a key extractor and a reduce function over whole
+//! items, api/reduce_by_key.hpp:312-363): the key is pair.first, the reduce function folds pair.second and keeps the key.
+struct KeyFirst {
+    template <typename P>
+    const typename P::first_type& operator () (const P& p) const { return p.first; }
+};
+template <typename ValueFunction>
+struct OnSecond {
+    ValueFunction fn;
+    template <typename P>
+    P operator () (const P& a, const P& b) const { return P(a.first, fn(a.second, b.second)); }
 };
 
 /******************************************************************************/
@@ -331,6 +385,20 @@ auto Sort(const DIA<ValueType, Stack>& dia, const CompareFunction& /* compare_fu
     return DIA<ValueType>(node);
 }
 
+//! DIA<T>::SortStable(cmp) (api/sort.hpp:873-937): equal keys keep their global input order.  The GPU sort is stable by
+//! construction (stable partition passes, exchange in worker order), so this is the same node with the flag set.
+template <typename ValueType, typename Stack, typename CompareFunction = std::less<ValueType> >
+auto SortStable(const DIA<ValueType, Stack>& dia, const CompareFunction& /* compare_function */ = CompareFunction()) {
+    static_assert(SortDesc<ValueType, CompareFunction>::supported,
+                  "thrill_gpu::SortStable: this (ValueType, CompareFunction) pair has no GPU descriptor; "
+                  "use the stock dia.SortStable(cmp)");
+    assert(dia.IsValid());
+    tg_key_desc d = SortDesc<ValueType, CompareFunction>::make();
+    d.stable = 1;
+    auto node = tlx::make_counting<GpuSortNode<ValueType> >(dia, d);
+    return DIA<ValueType>(node);
+}
+
 template <typename Key, typename Value, typename Stack, typename ReduceFunction>
 auto ReducePair(const DIA<std::pair<Key, Value>, Stack>& dia, const ReduceFunction& /* reduce_function */) {
     static_assert(std::is_same<Key, uint64_t>::value && sizeof(Value) == 8 &&
@@ -342,6 +410,16 @@ auto ReducePair(const DIA<std::pair<Key, Value>, Stack>& dia, const ReduceFuncti
     auto node = tlx::make_counting<GpuReduceNode<ValueType> >(
         dia, tg_kv_desc { 16, ReduceDesc<Value, ReduceFunction>::op });
     return DIA<ValueType>(node);
+}
+
+//! DIA<T>::ReduceByKey(key_extractor, reduce_function) (api/reduce_by_key.hpp:312-363) for the recognised functor pair:
+//! key_extractor = thrill_gpu::KeyFirst, reduce_function = thrill_gpu::OnSecond<F> with F one of the ReducePair functions
+//! (std::plus<double>, std::plus<uint64_t>, thrill_gpu::MinU64, thrill_gpu::MaxU64).  ReducePair is exactly this pair of
+//! functors in the reference too (:444-449).
+template <typename Key, typename Value, typename Stack, typename ValueFunction>
+auto ReduceByKey(const DIA<std::pair<Key, Value>, Stack>& dia, const KeyFirst& /* key_extractor */,
+                 const OnSecond<ValueFunction>& reduce_function) {
+    return ReducePair(dia, reduce_function.fn);
 }
 
 //! DIA<pair<uint64_t index, V>>::ReduceToIndex(key = .first, reduce function on .second, size, neutral_element)
