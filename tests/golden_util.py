@@ -13,5 +13,10 @@ def golden():
     return np.load(os.path.join(HERE, "golden", "reference_outputs.npz"))
 
 
+def golden_r2():
+    """larger cases (digests only), made by tests/golden/make_golden_r2.py from the unmodified reference"""
+    return np.load(os.path.join(HERE, "golden", "reference_outputs_r2.npz"))
+
+
 def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()

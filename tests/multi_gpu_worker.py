@@ -13,7 +13,7 @@ sys.path.insert(0, HERE)
 import torch.distributed as dist  # noqa: E402
 
 import oracle_lib as O  # noqa: E402
-from golden_util import golden, sha  # noqa: E402
+from golden_util import golden, golden_r2, sha  # noqa: E402
 from thrill_b200 import api, capi  # noqa: E402
 
 
@@ -79,6 +79,22 @@ def main():
         cat = np.concatenate(parts)
         assert np.array_equal(cat[:8], g["terasort_20000_w3_head"])
         assert sha(cat) == str(g["terasort_20000_w3_sha256"]), "terasort: differs from the reference"
+
+    # ---- round-2 fixtures: TeraSort 1e6 records and 5e6 Zipf(1, 2^20) keys, byte-identical to the reference ----
+    g2 = golden_r2()
+    dia = api.Generate(ctx, 1000000, lambda idx: O.gen_records(int(idx[0]) if len(idx) else 0, len(idx)), dtype=None)
+    parts = gather(dia.Sort().items, world)
+    if rank == 0:
+        cat = np.concatenate(parts)
+        assert np.array_equal(cat[:4], g2["terasort_1000000_head"]) and np.array_equal(cat[-4:], g2["terasort_1000000_tail"])
+        assert sha(cat) == str(g2["terasort_1000000_sha256"]), "terasort 1e6: differs from the reference"
+        assert max(len(q) for q in parts) <= 1.25 * 1000000 / world + 1000
+    cdf = O.zipf_cdf(1 << 20)
+    dia = api.Generate(ctx, 5000000, lambda idx: O.gen_sort_zipf(int(idx[0]) if len(idx) else 0, len(idx), cdf))
+    parts = gather(dia.Sort().items, world)
+    if rank == 0:
+        assert sha(np.concatenate(parts)) == str(g2["sort_zipf_u2^20_5000000_sha256"]), "sort zipf 5e6: differs from the reference"
+        assert max(len(q) for q in parts) <= 1.3 * 5000000 / world + 1000, [len(q) for q in parts]
 
     # ---- ReducePair: Zipf f64 sums vs the reference (tolerance) and exact mode (bit-exact), ownership ----
     cdf = O.zipf_cdf(4096)

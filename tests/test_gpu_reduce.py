@@ -228,3 +228,15 @@ def test_reduce_to_index_rejects_out_of_range_index(ctx):
     kv["key"] = np.arange(100); kv["key"][17] = 5000
     with pytest.raises(capi.ThrillGpuError):
         _reduce_to_index(ctx, kv, 1000, capi.OP_SUM_U64)
+
+
+def test_r2_golden_reduce_4e6_zipf_exact(ctx):
+    """ReducePair of 4e6 Zipf(1, 2^20) records in exact mode: digest of the key-sorted result equals the unmodified
+    reference's (tests/golden/reference_outputs_r2.npz); exercises the hot-key folding of the counting read"""
+    from thrill_b200 import capi
+    from golden_util import golden_r2, sha
+    g = golden_r2()
+    kv = O.gen_reduce_zipf(0, 4000000, O.zipf_cdf(1 << 20), exact=1)
+    out = _aggregate(ctx, kv, capi.OP_SUM_F64)
+    assert len(out) == int(g["reduce_f64_exact_zipf_u2^20_4000000_distinct"])
+    assert sha(out) == str(g["reduce_f64_exact_zipf_u2^20_4000000_sha256"])

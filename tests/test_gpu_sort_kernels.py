@@ -186,3 +186,36 @@ def test_terasort_records_single_gpu_golden(ctx):
     out2 = api.DIA(actx, rec2).Sort().items
     ref2 = O.sort_items(rec2, O.RECORD_DESC).reshape(-1, 100)
     assert np.array_equal(out2, ref2)
+
+
+def test_r2_golden_terasort_1e6_and_sort_1e7(ctx):
+    """larger reference outputs (tests/golden/reference_outputs_r2.npz): TeraSort 1e6 records, Sort 1e7 uniform keys and
+    5e6 Zipf(1, 2^20) keys, single GPU, byte-identical to the unmodified reference"""
+    from thrill_b200 import api
+    from golden_util import golden_r2
+    g = golden_r2()
+    actx = api.Context.__new__(api.Context)
+    actx._rank, actx._n, actx.tg, actx.rng_seed, actx._op_counter = 0, 1, ctx, 1, 0
+    out = api.DIA(actx, O.gen_records(0, 1000000)).Sort().items
+    assert np.array_equal(out[:4], g["terasort_1000000_head"]) and np.array_equal(out[-4:], g["terasort_1000000_tail"])
+    assert sha(out) == str(g["terasort_1000000_sha256"])
+    out = api.DIA(actx, O.gen_sort_uniform(0, 10000000)).Sort().items
+    assert sha(out) == str(g["sort_uniform_10000000_sha256"])
+    out = api.DIA(actx, O.gen_sort_zipf(0, 5000000, O.zipf_cdf(1 << 20))).Sort().items
+    assert sha(out) == str(g["sort_zipf_u2^20_5000000_sha256"])
+
+
+def test_terasort_full_size_properties(ctx):
+    """cfg4 per-GPU share, reduced to 2e7 records (2 GB): device-generated records, sorted by the 10-byte key, multiset kept"""
+    from thrill_b200 import capi
+    n = 20000000
+    d = ctx.alloc(n * 100)
+    ctx.ck(ctx.L.tg_gen_records(ctx.h, d, 0, n, 42))
+    before = ctx.checksum(d, n, 100)
+    desc = capi.record_desc()
+    op, on = C.c_void_p(), C.c_size_t()
+    ctx.ck(ctx.L.tg_sort(ctx.h, C.byref(desc), d, n, 5, C.byref(op), C.byref(on)))
+    assert on.value == n
+    assert ctx.is_sorted(desc, op.value, n)
+    assert ctx.checksum(op.value, n, 100) == before
+    ctx.free(d)

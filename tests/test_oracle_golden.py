@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
-from golden_util import REDUCE_OUT, golden, sha
+from golden_util import REDUCE_OUT, golden, golden_r2, sha
 
 
 def _counts(n, p):
@@ -164,3 +164,22 @@ def test_live_reference_reduce_to_index(workers, n, universe):
     assert len(ref) == universe
     mine = O.reduce_to_index(_rti_input("uniform", n, universe, 1), universe, O.OP_SUM_F64)
     assert np.array_equal(mine, ref)
+
+
+def test_golden_r2_larger_cases_pin_the_oracle():
+    """tests/golden/reference_outputs_r2.npz: TeraSort 1e6 records, Sort 1e7 uniform / 5e6 Zipf keys, ReducePair 4e6 Zipf
+    records (exact mode) of the unmodified reference vs the C restatement"""
+    g = golden_r2()
+    rec = O.gen_records(0, 1000000)
+    out = O.sort_items(rec, O.RECORD_DESC).reshape(-1, 100)
+    assert np.array_equal(out[:4], g["terasort_1000000_head"]) and np.array_equal(out[-4:], g["terasort_1000000_tail"])
+    assert sha(out) == str(g["terasort_1000000_sha256"])
+    keys = O.gen_sort_uniform(0, 10000000)
+    assert sha(O.sort_items(keys)) == str(g["sort_uniform_10000000_sha256"])
+    keys = O.gen_sort_zipf(0, 5000000, O.zipf_cdf(1 << 20))
+    out, _ = O.sort_operator(keys, _counts(5000000, 5))
+    assert sha(out) == str(g["sort_zipf_u2^20_5000000_sha256"])
+    kv = O.gen_reduce_zipf(0, 4000000, O.zipf_cdf(1 << 20), exact=1)
+    red = O.reduce_simple(kv, O.OP_SUM_F64)
+    assert len(red) == int(g["reduce_f64_exact_zipf_u2^20_4000000_distinct"])
+    assert sha(red) == str(g["reduce_f64_exact_zipf_u2^20_4000000_sha256"])

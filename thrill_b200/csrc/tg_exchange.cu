@@ -197,6 +197,16 @@ int xchg_upload_dest(tg_ctx* ctx, int item_bytes, const XchgResult& res, void***
     return TG_OK;
 }
 
+// after xchg_counts: this worker's items start at item before[d] of worker d's window
+void xchg_recv_offsets(tg_ctx* ctx, u64* before) {
+    const int p = ctx->nranks, me = ctx->rank;
+    const u32* h_mat = (const u32*)ctx->pinned + 16384;
+    for (int d = 0; d < p; ++d) {
+        before[d] = 0;
+        for (int src = 0; src < me; ++src) before[d] += h_mat[src * p + d];
+    }
+}
+
 void xwin_release(tg_ctx* ctx) {
     unmap_peers(ctx);
     if (ctx->xwin.base) cudaFree(ctx->xwin.base);

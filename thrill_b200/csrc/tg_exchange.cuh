@@ -33,6 +33,7 @@ int xwin_ensure(tg_ctx* ctx, size_t bytes_all_ranks);               // collectiv
 int xwin_barrier(tg_ctx* ctx);                                      // stream-ordered cross-rank barrier
 int xchg_counts(tg_ctx* ctx, const u32* d_totals, int item_bytes, XchgResult* res, u64* need_bytes_max);
 int xchg_upload_dest(tg_ctx* ctx, int item_bytes, const XchgResult& res, void*** d_dbase_out);
+void xchg_recv_offsets(tg_ctx* ctx, u64* before);                  // before[d] = items of the lower ranks in worker d's window
 
 // Stable partition of n local items by fn (destination worker, < p) + Alltoallv.  Collective.
 template <int WORDS, class DigitFn>

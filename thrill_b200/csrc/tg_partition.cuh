@@ -49,6 +49,7 @@ struct RadixDigit {
     int word, shift;
     u32 flip;
     static constexpr bool kStoreDigit = false;      // cheap to recompute in the write-out
+    static constexpr bool kHasDrop = false;         // true: digit RADIX-1 means "leave this item out of the output"
     __device__ __forceinline__ void init() {}
     template <class Item>
     __device__ __forceinline__ u32 operator()(const Item& v, u32) const {
@@ -462,6 +463,7 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
                     Item v = bufp[i * THREADS];
                     u32 d = DigitFn::kStoreDigit ? (u32)dig[i * THREADS + tid] : fn(v, 0);
                     if (DBG && (dbg & 8)) continue;
+                    if (DigitFn::kHasDrop && d == RADIX - 1) continue;
                     if (DBG && (dbg & 4)) out[tile_base + (u32)(i * THREADS + tid)] = v;
                     else if (PEER) dptr[d][goff[d] + (u32)(i * THREADS + tid)] = v;
                     else out[goff[d] + (u32)(i * THREADS + tid)] = v;
@@ -473,6 +475,7 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
                     if ((u32)(i * THREADS + tid) < tile_valid) {
                         Item v = bufp[i * THREADS];
                         u32 d = DigitFn::kStoreDigit ? (u32)dig[i * THREADS + tid] : fn(v, 0);
+                        if (DigitFn::kHasDrop && d == RADIX - 1) continue;
                         if (PEER) dptr[d][goff[d] + (u32)(i * THREADS + tid)] = v;
                         else out[goff[d] + (u32)(i * THREADS + tid)] = v;
                     }

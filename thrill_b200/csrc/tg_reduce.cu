@@ -160,6 +160,7 @@ compact_kernel(const ulonglong2* __restrict__ tab, u64 cap, ulonglong2* __restri
 struct HashDigit {
     u32 p;
     static constexpr bool kStoreDigit = true;
+    static constexpr bool kHasDrop = false;
     __device__ __forceinline__ void init() {}
     __device__ __forceinline__ u32 operator()(const ulonglong2& v, u32) const { return (u32)(key_hash(v.x) % p); }
 };
@@ -225,12 +226,14 @@ constexpr int AGG_THREADS = 256;
 constexpr int AGG_RPT = 8;                         // records per thread
 constexpr int AGG_UNIT = AGG_THREADS * AGG_RPT;    // 2048 records
 constexpr u32 AGG_SLOTS = 2 * AGG_UNIT;            // load factor <= 1/2
+constexpr u32 AGG_TAGS = 1024;                     // per-warp tag bytes of the in-warp leader election (agg_units_kernel)
 constexpr int AGG_SHIFT1 = 24, AGG_SHIFT2 = 32, AGG_SHIFT_SLOT = 40;
 constexpr size_t AGG_MIN_ITEMS = 1u << 18;         // below: the HBM table alone
 
 struct HashLevelDigit {
     int shift;
     static constexpr bool kStoreDigit = true;
+    static constexpr bool kHasDrop = false;
     __device__ __forceinline__ void init() {}
     __device__ __forceinline__ u32 operator()(const ulonglong2& v, u32) const { return (u32)(key_hash(v.x) >> shift) & (RADIX - 1); }
 };
@@ -267,6 +270,7 @@ agg_units_kernel(const ulonglong2* __restrict__ in, const uint2* __restrict__ un
     u32* const fill = scratch + 32;                                      // used slots of the table
     u64* const out_base = reinterpret_cast<u64*>(scratch + 34);          // reserved output position (8-byte aligned)
     uint4* const next_unit = reinterpret_cast<uint4*>(scratch + 36);     // [2] {unit id, first record, records|flags, -}, double buffered
+    unsigned char* const wtag = reinterpret_cast<unsigned char*>(next_unit + 2) + (threadIdx.x >> 5) * AGG_TAGS;   // [warps][AGG_TAGS] leader election
     const u32 lane = lane_id(), warp = threadIdx.x >> 5;
     constexpr int op = OP;             // compile-time: the reduce function's switch folds away
     constexpr int EI = AGG_SLOTS / AGG_THREADS;
@@ -367,31 +371,45 @@ agg_units_kernel(const ulonglong2* __restrict__ in, const uint2* __restrict__ un
                 // Lanes of the warp that carry the same key are reduced in registers first and one lane touches the table:
                 // records of a popular key sit next to each other here (their segment holds little else), and several lanes on
                 // one shared-memory CAS are replayed one after the other (measured: 5x the kernel time on Zipf keys).  Equal keys
-                // have equal home slots: group the lanes by the 12 slot bits (ballots); the lowest lane of a group speaks for
-                // the lanes that really have its key; all groups are reduced at once by pointer jumping along their lanes.
+                // have equal home slots.  A leader per home slot is elected through a small warp-private tag array (every lane
+                // stores its lane id at tag[home mod AGG_TAGS], then reads the survivor back): when every lane is its own leader
+                // — nearly every row of well-spread keys — nothing else is needed; otherwise the lanes are grouped by their
+                // leader's lane id (5 ballots), the leader speaks for the lanes that really have its key, and all groups are
+                // reduced at once by pointer jumping along their lanes.
                 u32 peers = __ballot_sync(0xffffffffu, mine);
                 if (!mine) peers = 0;
-#pragma unroll
-                for (int bit = 0; bit < 12; ++bit) {
-                    const bool one = (home >> bit) & 1u;
-                    const u32 m = __ballot_sync(0xffffffffu, one);
-                    peers &= one ? m : ~m;
+                u32 win = lane;
+                if (mine) {
+                    wtag[home & (AGG_TAGS - 1)] = (unsigned char)lane;
                 }
-                const int leader = mine ? __ffs(peers) - 1 : (int)lane;
-                const u64 kl = __shfl_sync(0xffffffffu, key[r], leader);
-                const bool follows = mine && key[r] == kl;                 // (a lane with another key in the same home slot: on its own)
-                const u32 samekey = __ballot_sync(0xffffffffu, follows);
-                const u32 group = follows ? (peers & samekey) : (mine ? (1u << lane) : 0u);
-                const bool leads = mine && ((group & ((1u << lane) - 1)) == 0);
-                if (__any_sync(0xffffffffu, (group & (group - 1)) != 0)) {
-                    const u32 above = group & ~((2u << lane) - 1u);
-                    int nxt = above ? __ffs(above) - 1 : -1;
+                __syncwarp();
+                if (mine) win = wtag[home & (AGG_TAGS - 1)];
+                __syncwarp();
+                bool leads = mine;
+                if (__any_sync(0xffffffffu, win != lane)) {
+                    // crowded row: group the lanes by their leader (5 ballots on its lane id)
 #pragma unroll
-                    for (int step = 0; step < 5; ++step) {
-                        const int src = nxt < 0 ? (int)lane : nxt;
-                        const u64 other = __shfl_sync(0xffffffffu, v, src);
-                        const int nn = __shfl_sync(0xffffffffu, nxt, src);
-                        if (nxt >= 0) { v = op_combine(op, v, other); nxt = nn; }
+                    for (int bit = 0; bit < 5; ++bit) {
+                        const bool one = (win >> bit) & 1u;
+                        const u32 m = __ballot_sync(0xffffffffu, one);
+                        peers &= one ? m : ~m;
+                    }
+                    const int leader = mine ? __ffs(peers) - 1 : (int)lane;
+                    const u64 kl = __shfl_sync(0xffffffffu, key[r], leader);
+                    const bool follows = mine && key[r] == kl;             // (a lane with another key in the same tag slot: on its own)
+                    const u32 samekey = __ballot_sync(0xffffffffu, follows);
+                    const u32 group = follows ? (peers & samekey) : (mine ? (1u << lane) : 0u);
+                    leads = mine && ((group & ((1u << lane) - 1)) == 0);
+                    if (__any_sync(0xffffffffu, (group & (group - 1)) != 0)) {
+                        const u32 above = group & ~((2u << lane) - 1u);
+                        int nxt = above ? __ffs(above) - 1 : -1;
+#pragma unroll
+                        for (int step = 0; step < 5; ++step) {
+                            const int src = nxt < 0 ? (int)lane : nxt;
+                            const u64 other = __shfl_sync(0xffffffffu, v, src);
+                            const int nn = __shfl_sync(0xffffffffu, nxt, src);
+                            if (nxt >= 0) { v = op_combine(op, v, other); nxt = nn; }
+                        }
                     }
                 }
                 if (!leads) continue;
@@ -431,6 +449,150 @@ agg_units_kernel(const ulonglong2* __restrict__ in, const uint2* __restrict__ un
         emit_and_clear(partial, nb ^ 1);
         cur = nxt_unit;
         nb ^= 1;
+    }
+}
+
+// ---- popular keys: reduced where the records are first read ------------------------------------------------------------
+// Under a skewed key distribution (Zipf s = 1: the 1000 most frequent of 6.7e7 keys carry 40 % of the records) most of the
+// traffic of the two partition passes moves records whose keys could have been folded on first sight — what the
+// reference's pre-phase table does for every key it can hold (core/reduce_pre_phase.hpp:167).  Here: a sample of the
+// input (HOT_SAMPLES records) is counted in a small HBM table, the keys seen at least 4 times (at most HOT_CAP, the most
+// frequent first) form the HOT TABLE; the counting read of the first pass (hot_hist_kernel) folds every record of a hot key
+// into CTA-private shared-memory accumulators, flushed to the table's accumulators at its end, and the first pass leaves
+// those records out (HotLevelDigit: digit RADIX-1 = drop).  The hot keys are appended to the result at the end.  Inputs
+// without popular keys (uniform keys over a large universe) find an empty table and skip the probing.
+constexpr u32 HOT_SLOTS = 2048, HOT_CAP = 1024, HOT_SAMPLES = 65536, HOT_STAB = 131072, HOT_MIN_COUNT = 4;
+constexpr int HOT_SHIFT = 52;
+struct HotTable {
+    u64 keys[HOT_SLOTS];        // open addressing, linear probing, 0 = empty (the key 0 is never hot)
+    u64 acc[HOT_SLOTS];
+    u32 nhot, threshold, pad0, pad1;
+};
+
+// slot of `key` in a hot table (keys in shared or global memory), or -1
+__device__ __forceinline__ int hot_find(const u64* __restrict__ keys, u64 key, u64 h) {
+    u32 slot = (u32)(h >> HOT_SHIFT) & (HOT_SLOTS - 1);
+    while (true) {
+        const u64 k = keys[slot];
+        if (k == key) return (int)slot;
+        if (k == 0) return -1;
+        slot = (slot + 1) & (HOT_SLOTS - 1);
+    }
+}
+
+__global__ void hot_sample_kernel(const ulonglong2* __restrict__ in, u64 n, u64* __restrict__ skeys, u32* __restrict__ scnt) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= HOT_SAMPLES) return;
+    const u64 key = in[(u64)i * n / HOT_SAMPLES].x;
+    if (key == 0) return;
+    u32 slot = (u32)(key_hash(key) >> 40) & (HOT_STAB - 1);
+    while (true) {
+        u64 k = skeys[slot];
+        if (k == 0) k = atomicCAS(&skeys[slot], 0ull, key);
+        if (k == 0 || k == key) { atomicAdd(&scnt[slot], 1u); return; }
+        slot = (slot + 1) & (HOT_STAB - 1);
+    }
+}
+
+// one CTA: threshold = smallest count >= HOT_MIN_COUNT that leaves at most HOT_CAP keys; those keys into the hot table
+__global__ void __launch_bounds__(1024) hot_select_kernel(const u64* __restrict__ skeys, const u32* __restrict__ scnt, HotTable* ht, u64 ident) {
+    __shared__ u32 hist[256];
+    __shared__ u32 thr;
+    for (int i = threadIdx.x; i < 256; i += 1024) hist[i] = 0;
+    __syncthreads();
+    for (u32 s = threadIdx.x; s < HOT_STAB; s += 1024) {
+        const u32 c = scnt[s];
+        if (c >= HOT_MIN_COUNT) atomicAdd(&hist[c < 255 ? c : 255], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 acc = 0, t = 256;
+        for (int c = 255; c >= (int)HOT_MIN_COUNT; --c) {
+            if (acc + hist[c] > HOT_CAP) break;
+            acc += hist[c];
+            t = (u32)c;
+        }
+        thr = t;
+        ht->threshold = t;
+    }
+    __syncthreads();
+    const u32 t = thr;
+    for (u32 s = threadIdx.x; s < HOT_STAB; s += 1024) {
+        if (scnt[s] < t) continue;
+        const u64 key = skeys[s];
+        u32 slot = (u32)(key_hash(key) >> HOT_SHIFT) & (HOT_SLOTS - 1);
+        while (atomicCAS(&ht->keys[slot], 0ull, key) != 0) slot = (slot + 1) & (HOT_SLOTS - 1);
+        ht->acc[slot] = ident;
+        atomicAdd(&ht->nhot, 1u);
+    }
+}
+
+// digit of the first pass (values 0..254 of the hash byte, rescaled) or RADIX-1 = a record of a hot key: dropped
+struct HotLevelDigit {
+    int shift;
+    const HotTable* ht;
+    u32 nhot;
+    static constexpr bool kStoreDigit = true;
+    static constexpr bool kHasDrop = true;
+    __device__ __forceinline__ void init() { nhot = ht->nhot; }
+    __device__ __forceinline__ u32 level(u64 h) const { return (((u32)(h >> shift) & (RADIX - 1)) * (RADIX - 1)) >> RADIX_BITS; }
+    __device__ __forceinline__ u32 operator()(const ulonglong2& v, u32) const {
+        const u64 h = key_hash(v.x);
+        if (nhot && v.x != 0 && hot_find(ht->keys, v.x, h) >= 0) return RADIX - 1;
+        return level(h);
+    }
+};
+
+// counting read of the first pass (the chunk_hist_kernel of tg_segmented.cuh) that also folds the records of hot keys:
+// chunkcount[chunk][d] for d < RADIX-1 = records of the chunk that the pass will move, [RADIX-1] = records folded here
+__global__ void __launch_bounds__(512) hot_hist_kernel(const ulonglong2* __restrict__ in, u32 n, u32 chunk_items, HotLevelDigit fn,
+                                                       int op, u64 ident, HotTable* ht, u32* __restrict__ chunkcount) {
+    constexpr int U = 4;
+    __shared__ u32 sh[RADIX];
+    __shared__ u64 hkeys[HOT_SLOTS];
+    __shared__ u64 hacc[HOT_SLOTS];
+    fn.init();
+    const bool hot = fn.nhot != 0;
+    for (int i = threadIdx.x; i < RADIX; i += blockDim.x) sh[i] = 0;
+    if (hot)
+        for (int i = threadIdx.x; i < (int)HOT_SLOTS; i += blockDim.x) { hkeys[i] = ht->keys[i]; hacc[i] = ident; }
+    __syncthreads();
+    const u32 lo = blockIdx.x * chunk_items;
+    const u32 hi = (n - lo < chunk_items) ? n : lo + chunk_items;
+    for (u32 base = lo; base < hi; base += blockDim.x * U) {
+        ulonglong2 v[U];
+        bool valid[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const u32 i = base + u * blockDim.x + threadIdx.x;
+            valid[u] = i < hi;
+            if (valid[u]) v[u] = in[i];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!valid[u]) continue;
+            const u64 h = key_hash(v[u].x);
+            int slot = -1;
+            if (hot && v[u].x != 0) slot = hot_find(hkeys, v[u].x, h);
+            if (slot >= 0) {
+                op_apply(op, &hacc[slot], v[u].y, false);
+                atomicAdd(&sh[RADIX - 1], 1u);
+            }
+            else atomicAdd(&sh[fn.level(h)], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < RADIX; i += blockDim.x) chunkcount[(size_t)blockIdx.x * RADIX + i] = sh[i];
+    if (hot)
+        for (int i = threadIdx.x; i < (int)HOT_SLOTS; i += blockDim.x)
+            if (hkeys[i] != 0 && hacc[i] != ident) op_apply(op, &ht->acc[i], hacc[i], false);
+}
+
+// the hot keys and their folded values appended to the output
+__global__ void __launch_bounds__(1024) hot_emit_kernel(const HotTable* ht, ulonglong2* __restrict__ out, u64* cursor) {
+    for (u32 s = threadIdx.x; s < HOT_SLOTS; s += 1024) {
+        const u64 k = ht->keys[s];
+        if (k != 0) out[atomicAdd(cursor, 1ull)] = make_ulonglong2(k, ht->acc[s]);
     }
 }
 
@@ -496,13 +658,49 @@ int run_partitioned_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 n, void
     void *bufA, *bufB;
     TG_TRY(tg_ws_get(ctx, WS_AUX, (n + 2) * 16, &bufA));
     TG_TRY(tg_ws_get(ctx, WS_AUX2, (n + 2) * 16, &bufB));
-    // (1) first hash digit: chunked pass
+    // (0) popular keys: sample, hot table (FIRST keeps the value of one arbitrary record: nothing to fold early)
+    const bool use_hot = op != TG_OP_FIRST && !getenv("TG_REDUCE_NO_HOT");
+    unsigned char* d_hot;
+    TG_TRY(tg_ws_get(ctx, WS_HOT, sizeof(HotTable) + (size_t)HOT_STAB * 12 + 64, (void**)&d_hot));
+    HotTable* ht = (HotTable*)d_hot;
+    u64* skeys = (u64*)(d_hot + sizeof(HotTable));
+    u32* scnt = (u32*)(skeys + HOT_STAB);
+    TG_CUDA(ctx, cudaMemsetAsync(d_hot, 0, sizeof(HotTable) + (size_t)HOT_STAB * 12, ctx->stream));
+    if (use_hot) {
+        TG_LAUNCH(ctx, hot_sample_kernel, HOT_SAMPLES / 256, 256, 0, (const ulonglong2*)d_in, n, skeys, scnt);
+        TG_LAUNCH(ctx, hot_select_kernel, 1, 1024, 0, (const u64*)skeys, (const u32*)scnt, ht, ident);
+    }
+    // (1) first hash digit: chunked pass; its counting read folds the records of the hot keys, the pass drops them
     u32 *d_tot1, *d_gbase1;
-    HashLevelDigit fn1 = { AGG_SHIFT1 };
-    TG_TRY((partition_chunked<2, HashLevelDigit>(ctx, d_in, bufA, n, fn1, &d_tot1, &d_gbase1)));
+    HotLevelDigit fn1 = { AGG_SHIFT1, ht, 0 };
+    {
+        const ChunkGeom g = chunk_geometry<2>(ctx, n);
+        const size_t cw = (size_t)g.nchunks * RADIX;
+        u32* tab;
+        TG_TRY(tg_ws_get(ctx, WS_SORT_HIST2, (2 * cw + 2 * RADIX + 16) * 4, (void**)&tab));
+        u32* chunkcount = tab;
+        u32* chunkbase = tab + cw;
+        d_tot1 = chunkbase + cw;
+        d_gbase1 = d_tot1 + RADIX;
+        TG_LAUNCH_T(ctx, TG_K_PREAGG, hot_hist_kernel, g.nchunks, 512, 0, (const ulonglong2*)d_in, (u32)n, g.chunk_items, fn1, op, ident, ht, chunkcount);
+        TG_LAUNCH(ctx, chunk_scan_kernel, 1, 4 * RADIX, 0, chunkcount, g.nchunks, d_tot1, d_gbase1, chunkbase);
+        std::vector<u32> chunk_size(g.nchunks, g.chunk_items);
+        chunk_size[g.nchunks - 1] = (u32)(n - (size_t)(g.nchunks - 1) * g.chunk_items);
+        uint4* d_ctiles;
+        u32 ctotal = 0;
+        TG_TRY(build_tile_list(ctx, g.nchunks, chunk_size.data(), tile_items<2>(), 0, WS_SEG_TILES2, &d_ctiles, &ctotal));
+        u32* cstatus;
+        TG_TRY(tg_ws_get(ctx, WS_SORT_STATUS, (size_t)ctotal * RADIX * 4, (void**)&cstatus));
+        TG_CUDA(ctx, cudaMemsetAsync(cstatus, 0, (size_t)ctotal * RADIX * 4, ctx->stream));
+        SegList csl = { d_ctiles, chunkbase, ctotal };
+        TG_TRY((launch_partition_seg<2, HotLevelDigit>(ctx, d_in, bufA, (u32)n, fn1, cstatus, csl)));
+    }
     u32* h_tot1 = (u32*)ctx->pinned;
     TG_CUDA(ctx, cudaMemcpyAsync(h_tot1, d_tot1, RADIX * 4, cudaMemcpyDeviceToHost, ctx->stream));
     TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const u64 n_hot = h_tot1[RADIX - 1];          // records folded by the counting read; the first pass left them out
+    h_tot1[RADIX - 1] = 0;
+    const u64 n_rest = n - n_hot;
     // (2) second hash digit inside the buckets of the first: segmented pass
     uint4* d_tiles;
     u32 total = 0;
@@ -525,7 +723,7 @@ int run_partitioned_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 n, void
     TG_TRY((launch_partition_seg<2, HashLevelDigit>(ctx, bufA, bufB, (u32)n, dl.fn[0], status, sl)));
     // (3) units of whole segments, built on the device from the segment table
     int group_log2 = 0;
-    while (group_log2 < 16 && ((u64)n << (group_log2 + 1)) / (RADIX * RADIX) <= (u64)AGG_UNIT / 2) ++group_log2;
+    while (group_log2 < 16 && ((u64)(n_rest ? n_rest : 1) << (group_log2 + 1)) / (RADIX * RADIX) <= (u64)AGG_UNIT / 2) ++group_log2;
     const size_t max_units = (table_words >> group_log2) + n / AGG_MAX_UNIT + 2;
     uint2* d_units;
     TG_TRY(tg_ws_get(ctx, WS_SEG_TILES2, max_units * sizeof(uint2) + 64, (void**)&d_units));
@@ -536,7 +734,7 @@ int run_partitioned_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 n, void
     u64* dup_cursor = sc.cursor + 1;
     ulonglong2* d_dup = (ulonglong2*)bufA;                     // the first pass's output is dead: reuse it for the partial aggregates
     const int agrid = ctx->sm_count * 3;
-    constexpr int AGG_SMEM = AGG_SLOTS * 16 + 36 * 4 + 2 * 16 + 32;
+    constexpr int AGG_SMEM = AGG_SLOTS * 16 + 36 * 4 + 2 * 16 + (AGG_THREADS / 32) * AGG_TAGS + 32;
 #define TG_AGG_LAUNCH(OPC)                                                                                              \
     case OPC: {                                                                                                         \
         auto kern = agg_units_kernel<OPC>;                                                                              \
@@ -563,7 +761,7 @@ int run_partitioned_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 n, void
     TG_CUDA(ctx, cudaMemcpyAsync(h, sc.cursor, 16, cudaMemcpyDeviceToHost, ctx->stream));
     TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const u64 ndup = h[1];
-    if (getenv("TG_DEBUG_REDUCE")) fprintf(stderr, "[tg_reduce] n=%llu group_log2=%d emitted=%llu partial aggregates=%llu\n", (unsigned long long)n, group_log2, (unsigned long long)h[0], (unsigned long long)ndup);
+    if (getenv("TG_DEBUG_REDUCE")) fprintf(stderr, "[tg_reduce] n=%llu hot records=%llu group_log2=%d emitted=%llu partial aggregates=%llu\n", (unsigned long long)n, (unsigned long long)n_hot, group_log2, (unsigned long long)h[0], (unsigned long long)ndup);
     // (4) merge the pieces of the long segments (and emit the zero key) through the HBM table, appended to d_out
     u64 cap = ndup ? ndup + ndup / 2 + 64 : 0;
     ulonglong2* tab = nullptr;
@@ -574,6 +772,7 @@ int run_partitioned_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 n, void
     }
     TG_LAUNCH_T(ctx, TG_K_COMPACT, compact_kernel, ndup ? ctx->sm_count * 4 : 1, ndup ? 512 : 32, 0, (const ulonglong2*)tab, cap,
                 (ulonglong2*)d_out, sc.cursor, sc.zero_slot);
+    if (n_hot) TG_LAUNCH(ctx, hot_emit_kernel, 1, 1024, 0, (const HotTable*)ht, (ulonglong2*)d_out, sc.cursor);
     return read_cursor(ctx, sc, out_distinct);
 }
 
@@ -584,6 +783,7 @@ struct RangeDigit {
     u64 size;
     u32 p;
     static constexpr bool kStoreDigit = true;
+    static constexpr bool kHasDrop = false;
     __device__ __forceinline__ void init() {}
     __device__ __forceinline__ u32 operator()(const ulonglong2& v, u32) const {
         return v.x < size ? (u32)(v.x * p / size) : p - 1;

@@ -39,6 +39,7 @@ struct SplitterDigit {
     KeyView kv;
     const u64* gbase_dev;          // if set: the worker's global index base, written by select_splitters_kernel
     static constexpr bool kStoreDigit = true;
+    static constexpr bool kHasDrop = false;
     __device__ __forceinline__ void init() { if (gbase_dev) gbase = *gbase_dev; }
     template <class Item>
     __device__ __forceinline__ u32 operator()(const Item& v, u32 pos) const {
@@ -327,30 +328,6 @@ bool classify_first() {
     return v != 0;
 }
 
-// splitters[i-1] = samples[(size_t)(i * double(S)/double(p))] over the (key, index)-sorted samples
-// (api/sort.hpp:357-372)
-// (only the p-1 order statistics are needed, not the sorted sample: nth_element on nested ranges instead of a full sort —
-// p * 2657 samples of 24 bytes cost ~2 ms to sort on the host at p = 8, on the critical path of every multi-worker sort)
-static void multi_select(CanonIdx* a, size_t lo, size_t hi, const size_t* pos, int np) {
-    if (np <= 0 || hi - lo < 2) return;
-    const int m = np / 2;
-    std::nth_element(a + lo, a + pos[m], a + hi, canonidx_less);
-    multi_select(a, lo, pos[m], pos, m);
-    multi_select(a, pos[m] + 1, hi, pos + m + 1, np - m - 1);
-}
-
-void pick_splitters(std::vector<CanonIdx>& samples, uint32_t p, std::vector<CanonIdx>* spl) {
-    spl->clear();
-    if (samples.empty()) return;
-    const double splitting_size = (double)samples.size() / (double)p;
-    std::vector<size_t> want, uniq;
-    for (uint32_t i = 1; i < p; ++i) want.push_back((size_t)((double)i * splitting_size));
-    for (size_t q : want)
-        if (uniq.empty() || uniq.back() != q) uniq.push_back(q);
-    multi_select(samples.data(), 0, samples.size(), uniq.data(), (int)uniq.size());
-    for (size_t q : want) spl->push_back(samples[q]);
-}
-
 // samples of every worker and the splitters, all on the device (no host round trip): d_spl[p-1] in LessSampleIndex order,
 // d_ctl = { this worker's global index base, total items, total samples, status flags }.  `items` are WORDS-word items whose
 // canonical key is described by kv.  Collective (one ncclAllGather).
@@ -518,33 +495,94 @@ int sort_multi_impl(tg_ctx* ctx, const tg_key_desc* desc, const KeyView& kv, voi
 
 
 // ---- records with payload (TeraSort: Record{uint8 key[10]; uint8 value[90]}, examples/terasort/terasort.cpp:31-42) ----
-// Sorted through 16-byte tuples {key bytes (<= 12, zero padded), u32 position}: build (read s, write 16), LSB radix
-// sort of the tuples (stable, so equal keys keep input order), one gather pass of the s-byte records.
-__global__ void make_tuples_kernel(const unsigned char* __restrict__ rec, u32 n, u32 item_bytes, u32 key_off, u32 key_bytes,
+// Sorted through 16-byte tuples {key bytes (<= 12, zero padded), u32 position}: build (reads only the sectors that hold the
+// keys, writes 16), radix sort of the tuples (stable, so equal keys keep input order), one gather pass of the s-byte records.
+// Records are a multiple of 4 bytes long and 4-byte aligned: every access below is a 32-bit word, consecutive threads on
+// consecutive words.
+
+// tuple i = { key bytes of record i, i }: one thread per record, the key read as the (<= 4) aligned words that cover it
+__global__ void make_tuples_kernel(const u32* __restrict__ rec, u32 n, u32 rec_words, u32 key_off, u32 key_bytes,
                                    ulonglong2* __restrict__ tuples) {
-    u32 stride = gridDim.x * blockDim.x;
+    const u32 stride = gridDim.x * blockDim.x;
+    const u32 w0 = key_off >> 2, sh = 8 * (key_off & 3), nw = (sh ? 1 : 0) + (key_bytes + 3) / 4;
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const unsigned char* r = rec + (size_t)i * item_bytes + key_off;
-        u64 w0 = 0, w1 = 0;
-        for (u32 j = 0; j < key_bytes && j < 8; ++j) w0 |= (u64)r[j] << (8 * j);
-        for (u32 j = 8; j < key_bytes; ++j) w1 |= (u64)r[j] << (8 * (j - 8));
-        w1 |= (u64)i << 32;                                  // bytes 12..15: position of the record
-        tuples[i] = make_ulonglong2(w0, w1);
+        const u32* r = rec + (size_t)i * rec_words + w0;
+        u32 x[5] = { 0, 0, 0, 0, 0 };
+#pragma unroll
+        for (u32 j = 0; j < 4; ++j)
+            if (j < nw && w0 + j < rec_words) x[j] = r[j];
+        u32 k[3];
+#pragma unroll
+        for (u32 j = 0; j < 3; ++j) k[j] = sh ? __funnelshift_r(x[j], x[j + 1], sh) : x[j];
+        // zero the bytes beyond the key
+        if (key_bytes < 12) {
+            const u32 full = key_bytes >> 2, rem = key_bytes & 3;
+#pragma unroll
+            for (u32 j = 0; j < 3; ++j) {
+                if (j > full || (j == full && rem == 0)) k[j] = 0;
+                else if (j == full) k[j] &= (1u << (8 * rem)) - 1;
+            }
+        }
+        tuples[i] = make_ulonglong2(((u64)k[1] << 32) | k[0], ((u64)i << 32) | k[2]);
     }
 }
 
-// out[j] = rec[tuples[j].position]; item_bytes is a multiple of 4: one warp moves a record with coalesced 4-byte words
-__global__ void gather_records_kernel(const unsigned char* __restrict__ rec, const ulonglong2* __restrict__ tuples, u32 n,
-                                      u32 item_bytes, unsigned char* __restrict__ out) {
-    const u32 words = item_bytes / 4;
-    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    const u32 lane = lane_id();
-    for (u32 j = warp; j < n; j += nwarps) {
-        u32 src = (u32)(tuples[j].y >> 32);
-        const u32* s4 = (const u32*)(rec + (size_t)src * item_bytes);
-        u32* d4 = (u32*)(out + (size_t)j * item_bytes);
-        for (u32 w = lane; w < words; w += 32) d4[w] = s4[w];
+// out record j = rec[tuples[j].position]: a CTA moves REC_BATCH consecutive output records per step, thread t the words
+// t, t + 256, ... of the batch (coalesced stores; the words of a record are read by consecutive threads).  Word index ->
+// (record, word) by a multiply-high with inv = floor(2^32 / rec_words) + 1 (exact below 2^32 / rec_words).
+constexpr u32 REC_BATCH = 1024;
+__global__ void __launch_bounds__(256) gather_records_kernel(const u32* __restrict__ rec, const ulonglong2* __restrict__ tuples,
+                                                              u32 n, u32 rec_words, u32 inv, u32* __restrict__ out) {
+    for (u32 r0 = blockIdx.x * REC_BATCH; r0 < n; r0 += gridDim.x * REC_BATCH) {
+        const u32 nrec = n - r0 < REC_BATCH ? n - r0 : REC_BATCH, words = nrec * rec_words;
+        u32* const o = out + (size_t)r0 * rec_words;
+#pragma unroll 4
+        for (u32 lt = threadIdx.x; lt < words; lt += 256) {
+            const u32 j = __umulhi(lt, inv), w = lt - j * rec_words;
+            const u32 src = (u32)(__ldg(&tuples[r0 + j].y) >> 32);
+            o[lt] = rec[(size_t)src * rec_words + w];
+        }
     }
+}
+
+// the exchange of the records: tuple g of the destination-partitioned tuple array names the record that becomes record
+// (g - first[d]) of this worker's share in destination d's window (dst[d], mapped peer memory or the local send buffer)
+struct RecDest {
+    u32* dst[TG_MAX_RANKS];
+    u32 first[TG_MAX_RANKS + 1];
+    int p;
+};
+__global__ void __launch_bounds__(256) scatter_records_kernel(const u32* __restrict__ rec, const ulonglong2* __restrict__ ptuples,
+                                                               u32 n, u32 rec_words, u32 inv, const RecDest rd) {
+    for (u32 r0 = blockIdx.x * REC_BATCH; r0 < n; r0 += gridDim.x * REC_BATCH) {
+        const u32 nrec = n - r0 < REC_BATCH ? n - r0 : REC_BATCH, words = nrec * rec_words;
+#pragma unroll 4
+        for (u32 lt = threadIdx.x; lt < words; lt += 256) {
+            const u32 j = __umulhi(lt, inv), w = lt - j * rec_words, g = r0 + j;
+            int d = 0;
+#pragma unroll
+            for (int q = 1; q < TG_MAX_RANKS; ++q) d += (q < rd.p && g >= rd.first[q]) ? 1 : 0;
+            const u32 src = (u32)(__ldg(&ptuples[g].y) >> 32);
+            rd.dst[d][(size_t)(g - rd.first[d]) * rec_words + w] = rec[(size_t)src * rec_words + w];
+        }
+    }
+}
+
+int sort_records_local(tg_ctx* ctx, const tg_key_desc* desc, const tg_key_desc& tdesc, const void* d_rec, size_t n, void** out_dptr) {
+    const u32 rb = desc->item_bytes;
+    ulonglong2* d_tup;
+    void* d_tmp;
+    TG_TRY(tg_ws_get(ctx, WS_AUX, (n + 1) * 16, (void**)&d_tup));
+    TG_TRY(tg_ws_get(ctx, WS_SORT_TMP, (n + 1) * 16, &d_tmp));
+    unsigned char* d_out;
+    TG_TRY(tg_ws_get(ctx, WS_OUT, (n + 1) * (size_t)rb, (void**)&d_out));
+    *out_dptr = d_out;
+    if (!n) return TG_OK;
+    TG_LAUNCH_T(ctx, TG_K_OTHER, make_tuples_kernel, ctx->sm_count * 8, 256, 0, (const u32*)d_rec, (u32)n, rb / 4, desc->key_offset, desc->key_bytes, d_tup);
+    void* d_stup;
+    TG_TRY(tg_radix_sort_items(ctx, &tdesc, d_tup, d_tmp, n, &d_stup));
+    TG_LAUNCH_T(ctx, TG_K_MERGE, gather_records_kernel, ctx->sm_count * 8, 256, 0, (const u32*)d_rec, (const ulonglong2*)d_stup, (u32)n, rb / 4, (u32)(0xffffffffu / (rb / 4)) + 1, (u32*)d_out);
+    return TG_OK;
 }
 
 int sort_records_impl(tg_ctx* ctx, const tg_key_desc* desc, void* d_in, size_t n_local, uint64_t rng_seed,
@@ -552,120 +590,77 @@ int sort_records_impl(tg_ctx* ctx, const tg_key_desc* desc, void* d_in, size_t n
     const u32 rb = desc->item_bytes;
     if (rb % 4 || desc->key_kind != TG_KEY_BYTES_BE || desc->key_bytes > 12 || desc->descending)
         return tg_set_error(ctx, TG_ERR_ARG, "sort: records need item_bytes %% 4 == 0 and an ascending byte-string key of <= 12 bytes");
-    if (n_local >= (1u << 30)) return tg_set_error(ctx, TG_ERR_TOO_LARGE, "sort: n_local=%zu", n_local);
+    if (((uintptr_t)d_in) & 3) return tg_set_error(ctx, TG_ERR_ARG, "sort: records must be 4-byte aligned");
     const int p = ctx->nranks, me = ctx->rank;
     tg_key_desc tdesc = { 16, 0, desc->key_bytes, TG_KEY_BYTES_BE, 0, 1 };
     KeyView tkv = { 0, desc->key_bytes, TG_KEY_BYTES_BE, 0 };
-    ulonglong2* d_tup;
-    void* d_tmp;
-    TG_TRY(tg_ws_get(ctx, WS_AUX, (n_local + 1) * 16, (void**)&d_tup));
-    TG_TRY(tg_ws_get(ctx, WS_SORT_TMP, (n_local + 1) * 16, &d_tmp));
-    if (n_local)
-        TG_LAUNCH(ctx, make_tuples_kernel, ctx->sm_count * 8, 256, 0, (const unsigned char*)d_in, (u32)n_local, rb, desc->key_offset, desc->key_bytes, d_tup);
-
     if (p == 1) {
-        void* d_stup;
-        TG_TRY(tg_radix_sort_items(ctx, &tdesc, d_tup, d_tmp, n_local, &d_stup));
-        unsigned char* d_out;
-        TG_TRY(tg_ws_get(ctx, WS_OUT, (n_local + 1) * (size_t)rb, (void**)&d_out));
-        if (n_local) TG_LAUNCH(ctx, gather_records_kernel, ctx->sm_count * 8, 256, 0, (const unsigned char*)d_in, (const ulonglong2*)d_stup, (u32)n_local, rb, d_out);
-        *out_dptr = d_out;
+        // workers_algo = 1 (api/sort.hpp:575-579): the local sort is the result
+        if (n_local >= (1u << 30)) return tg_set_error(ctx, TG_ERR_TOO_LARGE, "sort: n_local=%zu", n_local);
+        TG_TRY(sort_records_local(ctx, desc, tdesc, d_in, n_local, out_dptr));
         *out_n = n_local;
         return TG_OK;
     }
-
-    u64* h = (u64*)ctx->pinned;
+    // the reference's order (api/sort.hpp:615-742): classify by the splitters, exchange, sort what was received
+    const bool too_large = n_local >= (1u << 30);
+    const size_t n = too_large ? 0 : n_local;
+    TG_TRY(evacuate_window_input(ctx, &d_in, n * rb));
+    ulonglong2 *d_tup, *d_ptup;
+    TG_TRY(tg_ws_get(ctx, WS_AUX, (n + 1) * 16, (void**)&d_tup));
+    TG_TRY(tg_ws_get(ctx, WS_AUX2, (n + 1) * 16, (void**)&d_ptup));
+    if (n) TG_LAUNCH(ctx, make_tuples_kernel, ctx->sm_count * 8, 256, 0, (const u32*)d_in, (u32)n, rb / 4, desc->key_offset, desc->key_bytes, d_tup);
+    CanonIdx* d_spl;
     u64* d_ctl;
-    TG_TRY(tg_ws_get(ctx, WS_MISC, 1 << 16, (void**)&d_ctl));
-    h[0] = n_local;
-    TG_CUDA(ctx, cudaMemcpyAsync(d_ctl, h, 8, cudaMemcpyHostToDevice, ctx->stream));
-    TG_NCCL(ctx, ncclAllGather(d_ctl, d_ctl + 8, 1, ncclUint64, ctx->comm, ctx->stream));
-    TG_CUDA(ctx, cudaMemcpyAsync(h, d_ctl + 8, 8 * p, cudaMemcpyDeviceToHost, ctx->stream));
-    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    std::vector<u64> n_of(p);
-    u64 total = 0, prefix = 0;
-    for (int r = 0; r < p; ++r) { n_of[r] = h[r]; if (r < me) prefix += h[r]; total += h[r]; }
-    if (total == 0) { *out_dptr = nullptr; *out_n = 0; return TG_OK; }
-    std::vector<u32> ns_of(p);
-    u32 max_s = 1;
-    for (int r = 0; r < p; ++r) {
-        u64 want = n_of[r] ? tg_sample_size(n_of[r]) : 0;
-        ns_of[r] = (u32)(want < n_of[r] ? want : n_of[r]);
-        if (ns_of[r] > max_s) max_s = ns_of[r];
+    TG_TRY((device_splitters<2>(ctx, tkv, d_tup, n_local, rng_seed, too_large, &d_spl, &d_ctl)));
+    u64* h_ctl = (u64*)ctx->pinned + 3072;
+    TG_CUDA(ctx, cudaMemcpyAsync(h_ctl, d_ctl, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    SplitterDigit fn = { d_spl, (u32)(p - 1), 0, tkv, d_ctl };
+    TG_TRY(xwin_negotiate(ctx));
+    // destination histogram and the stable partition of the TUPLES by destination (local), then the records follow them
+    u32 *d_tot = nullptr, *d_gb = nullptr;
+    TG_TRY((partition_chunked<2, SplitterDigit>(ctx, d_tup, d_ptup, n, fn, &d_tot, &d_gb)));
+    XchgResult xr;
+    u64 need = 0;
+    TG_TRY(xchg_counts(ctx, d_tot, (int)rb, &xr, &need));                    // (synchronises; uniform verdicts)
+    if (h_ctl[3]) return tg_set_error(ctx, TG_ERR_TOO_LARGE, "sort: a worker holds 2^30 or more records");
+    if (h_ctl[1] == 0) { *out_dptr = nullptr; *out_n = 0; return TG_OK; }
+    TG_TRY(xwin_ensure(ctx, need));
+    RecDest rd;
+    rd.p = p;
+    u64 acc = 0;
+    for (int d = 0; d < TG_MAX_RANKS; ++d) {
+        rd.first[d] = (u32)acc;
+        if (d < p) acc += xr.send_cnt[d];
+        rd.dst[d] = nullptr;
     }
-    CanonIdx* d_samp;
-    TG_TRY(tg_ws_get(ctx, WS_SAMPLES, (size_t)(p + 1) * max_s * sizeof(CanonIdx) + 4096, (void**)&d_samp));
-    CanonIdx* d_mine = d_samp + (size_t)p * max_s;
-    if (ns_of[me])
-        TG_LAUNCH(ctx, draw_samples_kernel<2>, (ns_of[me] + 255) / 256, 256, 0, (const ulonglong2*)d_tup, (u64)n_local, prefix,
-                  rng_seed * 0x9E3779B97F4A7C15ull + (u64)me * 0x100000000ull, ns_of[me], tkv, (ulonglong2*)nullptr, d_mine);
-    TG_NCCL(ctx, ncclAllGather(d_mine, d_samp, (size_t)max_s * sizeof(CanonIdx), ncclUint8, ctx->comm, ctx->stream));
-    std::vector<CanonIdx> all((size_t)p * max_s);
-    TG_CUDA(ctx, cudaMemcpyAsync(all.data(), d_samp, all.size() * sizeof(CanonIdx), cudaMemcpyDeviceToHost, ctx->stream));
-    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    std::vector<CanonIdx> samples, spl;
-    for (int r = 0; r < p; ++r)
-        for (u32 i = 0; i < ns_of[r]; ++i) samples.push_back(all[(size_t)r * max_s + i]);
-    pick_splitters(samples, (uint32_t)p, &spl);
-    const u32 nspl = (u32)spl.size();
-    CanonIdx* d_spl = d_samp;
-    u32* d_tie = (u32*)(d_ctl + 1024);
-    u64* d_bnd = d_ctl + 2048;
-    TG_CUDA(ctx, cudaMemcpyAsync(d_spl, spl.data(), nspl * sizeof(CanonIdx), cudaMemcpyHostToDevice, ctx->stream));
-    TG_CUDA(ctx, cudaMemsetAsync(d_tie, 0, 4096, ctx->stream));
-    if (n_local && nspl)
-        TG_LAUNCH(ctx, tie_count_kernel<2>, ctx->sm_count * 4, 512, 0, (const ulonglong2*)d_tup, (u32)n_local, prefix, tkv, d_spl, nspl, d_tie);
-    void* d_stup;
-    TG_TRY(tg_radix_sort_items(ctx, &tdesc, d_tup, d_tmp, n_local, &d_stup));
-    if (nspl) TG_LAUNCH(ctx, boundaries_kernel<2>, (nspl + 63) / 64, 64, 0, (const ulonglong2*)d_stup, (u32)n_local, tkv, d_spl, nspl, d_tie, d_bnd);
-    TG_CUDA(ctx, cudaMemcpyAsync(h, d_bnd, 8 * nspl, cudaMemcpyDeviceToHost, ctx->stream));
-    // locally sorted records (the run this worker contributes)
-    unsigned char* d_sorted;
-    TG_TRY(tg_ws_get(ctx, WS_XCHG_SEND, (n_local + 1) * (size_t)rb, (void**)&d_sorted));
-    if (n_local) TG_LAUNCH(ctx, gather_records_kernel, ctx->sm_count * 8, 256, 0, (const unsigned char*)d_in, (const ulonglong2*)d_stup, (u32)n_local, rb, d_sorted);
-    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    std::vector<u64> send_cnt(p), send_off(p + 1, 0);
-    {
-        u64 prev = 0;
-        for (int r = 0; r < p; ++r) {
-            u64 b = (r < p - 1) ? h[r] : n_local;
-            send_cnt[r] = b - prev;
-            prev = b;
-            send_off[r + 1] = send_off[r] + send_cnt[r];
-        }
+    rd.first[TG_MAX_RANKS] = (u32)acc;
+    const int xprof = ctx->profile ? tg_prof_begin(ctx, TG_K_EXCHANGE) : -1;
+    if (ctx->xwin.mode == 1) {
+        u64 before[TG_MAX_RANKS];
+        xchg_recv_offsets(ctx, before);
+        for (int d = 0; d < p; ++d) rd.dst[d] = (u32*)((char*)ctx->xwin.peer[d] + before[d] * rb);
+        if (n) TG_LAUNCH(ctx, scatter_records_kernel, ctx->sm_count * 8, 256, 0, (const u32*)d_in, (const ulonglong2*)d_ptup, (u32)n, rb / 4, (u32)(0xffffffffu / (rb / 4)) + 1, rd);
+        TG_TRY(xwin_barrier(ctx));
     }
-    for (int r = 0; r < p; ++r) h[r] = send_cnt[r];
-    TG_CUDA(ctx, cudaMemcpyAsync(d_ctl, h, 8 * p, cudaMemcpyHostToDevice, ctx->stream));
-    TG_NCCL(ctx, ncclAllGather(d_ctl, d_ctl + 64, p, ncclUint64, ctx->comm, ctx->stream));
-    TG_CUDA(ctx, cudaMemcpyAsync(h, d_ctl + 64, 8 * p * p, cudaMemcpyDeviceToHost, ctx->stream));
-    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    std::vector<u64> recv_cnt(p), recv_off(p + 1, 0);
-    for (int r = 0; r < p; ++r) { recv_cnt[r] = h[(size_t)r * p + me]; recv_off[r + 1] = recv_off[r] + recv_cnt[r]; }
-    const u64 n_recv = recv_off[p];
-    if (n_recv >= (1u << 30)) return tg_set_error(ctx, TG_ERR_TOO_LARGE, "sort: received %llu records", n_recv);
-    unsigned char* d_recv;
-    TG_TRY(tg_ws_get(ctx, WS_XCHG_RECV, (n_recv + 1) * (size_t)rb, (void**)&d_recv));
-    const int xprof_ = ctx->profile ? tg_prof_begin(ctx, TG_K_EXCHANGE) : -1;
+    else {
+        char* d_send;
+        TG_TRY(tg_ws_get(ctx, WS_XCHG_SEND, (n + 1) * (size_t)rb, (void**)&d_send));
+        for (int d = 0; d < p; ++d) rd.dst[d] = (u32*)(d_send + (size_t)rd.first[d] * rb);
+        if (n) TG_LAUNCH(ctx, scatter_records_kernel, ctx->sm_count * 8, 256, 0, (const u32*)d_in, (const ulonglong2*)d_ptup, (u32)n, rb / 4, (u32)(0xffffffffu / (rb / 4)) + 1, rd);
         TG_NCCL(ctx, ncclGroupStart());
-    for (int r = 0; r < p; ++r) {
-        if (send_cnt[r]) TG_NCCL(ctx, ncclSend(d_sorted + send_off[r] * rb, send_cnt[r] * rb, ncclUint8, r, ctx->comm, ctx->stream));
-        if (recv_cnt[r]) TG_NCCL(ctx, ncclRecv(d_recv + recv_off[r] * rb, recv_cnt[r] * rb, ncclUint8, r, ctx->comm, ctx->stream));
+        u64 roff = 0;
+        for (int r = 0; r < p; ++r) {
+            if (xr.send_cnt[r]) TG_NCCL(ctx, ncclSend(d_send + (size_t)rd.first[r] * rb, xr.send_cnt[r] * rb, ncclUint8, r, ctx->comm, ctx->stream));
+            if (xr.recv_cnt[r]) TG_NCCL(ctx, ncclRecv((char*)ctx->xwin.base + roff * rb, xr.recv_cnt[r] * rb, ncclUint8, r, ctx->comm, ctx->stream));
+            roff += xr.recv_cnt[r];
+        }
+        TG_NCCL(ctx, ncclGroupEnd());
     }
-    TG_NCCL(ctx, ncclGroupEnd());
-        if (xprof_ >= 0) tg_prof_end(ctx, xprof_);
-    // merge the received runs through their tuples, then gather
-    ulonglong2* d_rtup;
-    ulonglong2* d_mtup;
-    TG_TRY(tg_ws_get(ctx, WS_AUX, (n_recv + 1) * 16, (void**)&d_rtup));
-    TG_TRY(tg_ws_get(ctx, WS_AUX2, (n_recv + 1) * 16, (void**)&d_mtup));
-    TG_TRY(tg_ws_get(ctx, WS_SORT_TMP, (n_recv + 1) * 16, &d_tmp));
-    if (n_recv) TG_LAUNCH(ctx, make_tuples_kernel, ctx->sm_count * 8, 256, 0, (const unsigned char*)d_recv, (u32)n_recv, rb, desc->key_offset, desc->key_bytes, d_rtup);
-    TG_TRY(merge_runs_impl<2>(ctx, tkv, d_rtup, (const uint64_t*)recv_cnt.data(), (uint32_t)p, d_mtup, d_tmp));
-    unsigned char* d_out;
-    TG_TRY(tg_ws_get(ctx, WS_OUT, (n_recv + 1) * (size_t)rb, (void**)&d_out));
-    if (n_recv) TG_LAUNCH(ctx, gather_records_kernel, ctx->sm_count * 8, 256, 0, (const unsigned char*)d_recv, d_mtup, (u32)n_recv, rb, d_out);
-    *out_dptr = d_out;
-    *out_n = (size_t)n_recv;
+    if (xprof >= 0) tg_prof_end(ctx, xprof);
+    (void)me;
+    // ReceiveItems + SortAndWriteToFile (:665-742) on the received records (grouped by source worker in worker order)
+    TG_TRY(sort_records_local(ctx, desc, tdesc, ctx->xwin.base, xr.n_recv, out_dptr));
+    *out_n = (size_t)xr.n_recv;
     return TG_OK;
 }
 
