@@ -185,6 +185,23 @@ __device__ __forceinline__ void rank_rows(const Item (&key)[ITEMS], u32 (&rank)[
     }
 }
 
+// Ranking for passes that need not be stable (items that are nothing but their key: equal keys are indistinguishable, and the
+// pass is the first one on its part of the key — the most significant digit, or the first of the digits below it): every lane
+// takes its rank from a shared-memory atomic on its digit's warp-private counter (two 16-bit counters per 32-bit word).  One
+// ATOMS on the ADU pipe replaces the 28-instruction ballot match and the counter read/write on the ALU pipe, the busiest one
+// of this kernel (profiles/r2_partition_pass_u64.txt).
+template <int ITEMS, class Item, class DigitFn>
+__device__ __forceinline__ void rank_rows_unstable(const Item (&key)[ITEMS], u32 (&rank)[ITEMS], const DigitFn& fn, u32 whist_w) {
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const u32 d = fn(key[i], 0);
+        const u32 sh = (d & 1u) << 4;
+        u32 old;
+        asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(whist_w + (d >> 1) * 4u), "r"(1u << sh) : "memory");
+        rank[i] = (old >> sh) & 0xffffu;
+    }
+}
+
 // Segmented operation: the input is a sequence of independent segments (e.g. the 256 buckets of a previous pass on
 // a more significant digit); every segment is partitioned on its own, with its own bases and its own chained scan.
 // The host lists the tiles in an order that interleaves the segments, so the tile a tile's scan depends on (the
@@ -203,7 +220,8 @@ struct SegList {
 // PEER: the buckets are destination workers; bucket d is written to dbase[d][position], where dbase[d] points into worker
 // d's exchange window (mapped peer memory: the stores travel over NVLink) biased so that `position` is the position the
 // plain pass would have used in `out` — the Alltoallv of the reference's MixStream exchange happens inside the pass.
-template <int WORDS, int THREADS, int IPT, int MINB, class DigitFn, bool SEG, bool DBG = false, bool TMA = true, bool PEER = false>
+template <int WORDS, int THREADS, int IPT, int MINB, class DigitFn, bool SEG, bool DBG = false, bool TMA = true, bool PEER = false,
+          bool UNSTABLE = false>
 __global__ void __launch_bounds__(THREADS, MINB)
 partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename ItemT<WORDS>::type* __restrict__ out,
                  u32 n, const DigitFn fn_param, const u32* __restrict__ gbase, u32* __restrict__ status, const SegList sl,
@@ -338,7 +356,8 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
         __syncwarp();
 
         // ---- stable rank inside the warp (partial tiles always carry the digit along: padding has none)
-        if (full_tile) rank_rows<true, DigitFn::kStoreDigit>(key, rank, fn, whist_w_a, wbase + lane, tile_base, tile_valid, lt, DBG && (dbg & 2));
+        if (full_tile && UNSTABLE && !DigitFn::kStoreDigit) rank_rows_unstable(key, rank, fn, whist_w_a);
+        else if (full_tile) rank_rows<true, DigitFn::kStoreDigit>(key, rank, fn, whist_w_a, wbase + lane, tile_base, tile_valid, lt, DBG && (dbg & 2));
         else rank_rows<false, true>(key, rank, fn, whist_w_a, wbase + lane, tile_base, tile_valid, lt);
         __syncthreads();      // all items are in registers (buf is free), all warp counters final
 
@@ -521,13 +540,14 @@ inline int sweep_debug() {
     return f;
 }
 
-template <int WORDS, int THREADS, int WPT, int MINB, class DigitFn, bool SEG = false, bool DBG = false, bool TMA = true, bool PEER = false>
+template <int WORDS, int THREADS, int WPT, int MINB, class DigitFn, bool SEG = false, bool DBG = false, bool TMA = true, bool PEER = false,
+          bool UNSTABLE = false>
 int launch_partition_v(tg_ctx* ctx, const void* in, void* out, u32 n, const DigitFn& fn, const u32* gbase, u32* status,
                        const SegList& sl = SegList{ nullptr, nullptr, 0 }, typename ItemT<WORDS>::type* const* dbase = nullptr) {
     typedef typename ItemT<WORDS>::type Item;
     constexpr int IPT = WPT / WORDS;
     typedef SweepCfg<WORDS, THREADS, IPT, TMA, DigitFn::kStoreDigit, PEER> C;
-    auto kern = partition_kernel<WORDS, THREADS, IPT, MINB, DigitFn, SEG, DBG, TMA, PEER>;
+    auto kern = partition_kernel<WORDS, THREADS, IPT, MINB, DigitFn, SEG, DBG, TMA, PEER, UNSTABLE>;
     int ctas_per_sm = 0;
     auto it = ctx->kernel_cfg.find((const void*)kern);
     if (it != ctx->kernel_cfg.end()) ctas_per_sm = it->second;
@@ -599,6 +619,17 @@ int launch_partition_seg(tg_ctx* ctx, const void* in, void* out, u32 n, const Di
     case 9: return launch_partition_v<WORDS, 256, 16, 4, DigitFn, true, false, false>(ctx, in, out, n, fn, nullptr, status, sl);
     case 10: return launch_partition_v<WORDS, 512, 16, 2, DigitFn, true, false, false>(ctx, in, out, n, fn, nullptr, status, sl);
     default: return launch_partition_v<WORDS, 512, 16, 1, DigitFn, true>(ctx, in, out, n, fn, nullptr, status, sl);
+    }
+}
+
+// one segmented pass that need not be stable (see rank_rows_unstable); launch configurations 0-2, the others run the stable pass
+template <int WORDS, class DigitFn>
+int launch_partition_seg_unstable(tg_ctx* ctx, const void* in, void* out, u32 n, const DigitFn& fn, u32* status, const SegList& sl) {
+    switch (sweep_cfg()) {
+    case 0: return launch_partition_v<WORDS, 512, 16, 1, DigitFn, true, false, true, false, true>(ctx, in, out, n, fn, nullptr, status, sl);
+    case 1: return launch_partition_v<WORDS, 256, 16, 2, DigitFn, true, false, true, false, true>(ctx, in, out, n, fn, nullptr, status, sl);
+    case 2: return launch_partition_v<WORDS, 256, 16, 3, DigitFn, true, false, true, false, true>(ctx, in, out, n, fn, nullptr, status, sl);
+    default: return launch_partition_seg<WORDS, DigitFn>(ctx, in, out, n, fn, status, sl);
     }
 }
 

@@ -304,9 +304,11 @@ bool segmented_enabled() {
 
 // `npos` stable passes (digit positions pos[0..npos), least significant first) inside the segments given by the
 // histogram of the digit the items are currently partitioned by (seg_size on the host, seg_start on the device)
+// first_unstable: the first of these passes orders by a digit below which nothing has been ordered yet, and the items are
+// nothing but their key: it may run with the cheaper unstable ranking
 template <int WORDS>
 int run_segmented_passes(tg_ctx* ctx, const PassList& pl, const int* pos, int npos, const u32* seg_size,
-                         const u32* d_seg_start, size_t n, void** src, void** dst) {
+                         const u32* d_seg_start, size_t n, void** src, void** dst, bool first_unstable = false) {
     typedef typename ItemT<WORDS>::type Item;
     if (npos == 0) return TG_OK;
     if (npos > 4) return tg_set_error(ctx, TG_ERR_ARG, "segmented passes: at most 4 digit positions");
@@ -338,7 +340,10 @@ int run_segmented_passes(tg_ctx* ctx, const PassList& pl, const int* pos, int np
     for (int i = 0; i < npos; ++i) {
         RadixDigit fn = { (int)pl.word[pos[i]], (int)pl.shift[pos[i]], pl.flip };
         sl.segbase = segbase + (size_t)i * RADIX * RADIX;
-        TG_TRY((launch_partition_seg<WORDS, RadixDigit>(ctx, *src, *dst, (u32)n, fn, status + (size_t)i * pass_status_words, sl)));
+        if (i == 0 && first_unstable)
+            TG_TRY((launch_partition_seg_unstable<WORDS, RadixDigit>(ctx, *src, *dst, (u32)n, fn, status + (size_t)i * pass_status_words, sl)));
+        else
+            TG_TRY((launch_partition_seg<WORDS, RadixDigit>(ctx, *src, *dst, (u32)n, fn, status + (size_t)i * pass_status_words, sl)));
         void* t = *src; *src = *dst; *dst = t;
     }
     return TG_OK;
@@ -462,14 +467,19 @@ int prefix_sort_fast(tg_ctx* ctx, const tg_key_desc* desc, const PassList& pl, b
         for (int i = 0; i < K - 1; ++i) prefix_pos[i] = active[nactive - K + i];
         pm = prefix_mask(desc, active[nactive - K]);
     }
+    // Items that are nothing but their key (equal keys are indistinguishable) need no stability from the pass on the most
+    // significant digit nor from the first pass below it: the cheaper unstable ranking (TG_UNSTABLE_RANK=0 switches it off)
+    static const bool unstable_ok = !(getenv("TG_UNSTABLE_RANK") && atoi(getenv("TG_UNSTABLE_RANK")) == 0);
+    const bool key_only = unstable_ok && desc->key_bytes == desc->item_bytes && desc->key_offset == 0;
     // (1) most significant digit: segmented pass over the chunks
     {
         SegList sl = { d_ctiles, chunkbase, ctotal };
-        TG_TRY((launch_partition_seg<WORDS, RadixDigit>(ctx, *src, *dst, (u32)n, top_fn, cstatus, sl)));
+        if (key_only) TG_TRY((launch_partition_seg_unstable<WORDS, RadixDigit>(ctx, *src, *dst, (u32)n, top_fn, cstatus, sl)));
+        else TG_TRY((launch_partition_seg<WORDS, RadixDigit>(ctx, *src, *dst, (u32)n, top_fn, cstatus, sl)));
         void* t = *src; *src = *dst; *dst = t;
     }
     // (2) the other K-1 prefix digits inside the buckets of (1)
-    TG_TRY((run_segmented_passes<WORDS>(ctx, pp, prefix_pos, K - 1, h_totals, gbase_top, n, src, dst)));
+    TG_TRY((run_segmented_passes<WORDS>(ctx, pp, prefix_pos, K - 1, h_totals, gbase_top, n, src, dst, key_only)));
     // (3) finishing pass
     bool ok = false;
     TG_TRY((run_fixup<WORDS>(ctx, desc, plain_u64, pm, *src, *dst, n, fail, &ok)));

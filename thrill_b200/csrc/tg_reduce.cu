@@ -461,20 +461,33 @@ agg_units_kernel(const ulonglong2* __restrict__ in, const uint2* __restrict__ un
 // into CTA-private shared-memory accumulators, flushed to the table's accumulators at its end, and the first pass leaves
 // those records out (HotLevelDigit: digit RADIX-1 = drop).  The hot keys are appended to the result at the end.  Inputs
 // without popular keys (uniform keys over a large universe) find an empty table and skip the probing.
-constexpr u32 HOT_SLOTS = 2048, HOT_CAP = 1024, HOT_SAMPLES = 65536, HOT_STAB = 131072, HOT_MIN_COUNT = 4;
+constexpr u32 HOT_SLOTS = 4096, HOT_CAP = 1024, HOT_SAMPLES = 65536, HOT_STAB = 131072, HOT_MIN_COUNT = 4;
+constexpr u32 HOT_SUPER = 64;        // the most frequent hot keys get warp-private accumulators in the counting read
 constexpr int HOT_SHIFT = 52;
+constexpr int HOT_HIST_THREADS = 512;
 struct HotTable {
-    u64 keys[HOT_SLOTS];        // open addressing, linear probing, 0 = empty (the key 0 is never hot)
+    u64 keys[HOT_SLOTS];            // open addressing, linear probing (load <= 1/4), 0 = empty (the key 0 is never hot)
+    u64 hashes[HOT_SLOTS];          // Hash128to64(0, key) of the slot's key: the hash is a bijection of the key (odd multiplications
+                                    // and xor-shifts), so probing compares hashes — which every record has computed anyway; 0 = empty
     u64 acc[HOT_SLOTS];
-    u32 nhot, threshold, pad0, pad1;
+    u32 super_slot[HOT_SUPER];      // slot of super-hot key j
+    unsigned char super_idx[HOT_SLOTS];   // 0xff, or j: this slot holds super-hot key j
+    u32 nhot, threshold, nsuper, super_threshold;
 };
 
-// slot of `key` in a hot table (keys in shared or global memory), or -1
-__device__ __forceinline__ int hot_find(const u64* __restrict__ keys, u64 key, u64 h) {
+// slot of the key with hash h in a hot table (hashes in shared memory), or -1.  Two probes without a branch back (at load
+// 1/4 nearly every search ends there, and the lanes of a warp stay together), then the general loop.
+__device__ __forceinline__ int hot_find(const u64* __restrict__ hashes, u64 h) {
     u32 slot = (u32)(h >> HOT_SHIFT) & (HOT_SLOTS - 1);
+    const u64 k0 = hashes[slot], k1 = hashes[(slot + 1) & (HOT_SLOTS - 1)];
+    if (k0 == h) return (int)slot;
+    if (k0 == 0) return -1;
+    if (k1 == h) return (int)((slot + 1) & (HOT_SLOTS - 1));
+    if (k1 == 0) return -1;
+    slot = (slot + 2) & (HOT_SLOTS - 1);
     while (true) {
-        const u64 k = keys[slot];
-        if (k == key) return (int)slot;
+        const u64 k = hashes[slot];
+        if (k == h) return (int)slot;
         if (k == 0) return -1;
         slot = (slot + 1) & (HOT_SLOTS - 1);
     }
@@ -494,11 +507,13 @@ __global__ void hot_sample_kernel(const ulonglong2* __restrict__ in, u64 n, u64*
     }
 }
 
-// one CTA: threshold = smallest count >= HOT_MIN_COUNT that leaves at most HOT_CAP keys; those keys into the hot table
+// one CTA: threshold = smallest count >= HOT_MIN_COUNT that leaves at most HOT_CAP keys (HOT_SUPER for the super-hot ones);
+// those keys into the hot table
 __global__ void __launch_bounds__(1024) hot_select_kernel(const u64* __restrict__ skeys, const u32* __restrict__ scnt, HotTable* ht, u64 ident) {
     __shared__ u32 hist[256];
-    __shared__ u32 thr;
+    __shared__ u32 thr, thr2;
     for (int i = threadIdx.x; i < 256; i += 1024) hist[i] = 0;
+    for (u32 s = threadIdx.x; s < HOT_SLOTS; s += 1024) ht->super_idx[s] = 0xff;
     __syncthreads();
     for (u32 s = threadIdx.x; s < HOT_STAB; s += 1024) {
         const u32 c = scnt[s];
@@ -506,56 +521,77 @@ __global__ void __launch_bounds__(1024) hot_select_kernel(const u64* __restrict_
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        u32 acc = 0, t = 256;
+        u32 acc = 0, t = 256, t2 = 256;
         for (int c = 255; c >= (int)HOT_MIN_COUNT; --c) {
             if (acc + hist[c] > HOT_CAP) break;
             acc += hist[c];
             t = (u32)c;
+            if (acc <= HOT_SUPER) t2 = (u32)c;
         }
-        thr = t;
+        thr = t; thr2 = t2;
         ht->threshold = t;
+        ht->super_threshold = t2;
     }
     __syncthreads();
-    const u32 t = thr;
+    const u32 t = thr, t2 = thr2;
     for (u32 s = threadIdx.x; s < HOT_STAB; s += 1024) {
-        if (scnt[s] < t) continue;
+        const u32 c = scnt[s];
+        if (c < t) continue;
         const u64 key = skeys[s];
         u32 slot = (u32)(key_hash(key) >> HOT_SHIFT) & (HOT_SLOTS - 1);
         while (atomicCAS(&ht->keys[slot], 0ull, key) != 0) slot = (slot + 1) & (HOT_SLOTS - 1);
+        ht->hashes[slot] = key_hash(key);
         ht->acc[slot] = ident;
         atomicAdd(&ht->nhot, 1u);
+        if (c >= t2) {
+            const u32 j = atomicAdd(&ht->nsuper, 1u);          // (at most HOT_SUPER keys reach t2)
+            ht->super_slot[j] = slot;
+            ht->super_idx[slot] = (unsigned char)j;
+        }
     }
 }
 
-// digit of the first pass (values 0..254 of the hash byte, rescaled) or RADIX-1 = a record of a hot key: dropped
+// digit of the first pass (values 0..254 of the hash byte, rescaled) or RADIX-1 = a record of a hot key, which the counting
+// read has folded and marked in `mask` (one bit per record): dropped
 struct HotLevelDigit {
     int shift;
     const HotTable* ht;
+    const u32* mask;
     u32 nhot;
     static constexpr bool kStoreDigit = true;
     static constexpr bool kHasDrop = true;
     __device__ __forceinline__ void init() { nhot = ht->nhot; }
     __device__ __forceinline__ u32 level(u64 h) const { return (((u32)(h >> shift) & (RADIX - 1)) * (RADIX - 1)) >> RADIX_BITS; }
-    __device__ __forceinline__ u32 operator()(const ulonglong2& v, u32) const {
-        const u64 h = key_hash(v.x);
-        if (nhot && v.x != 0 && hot_find(ht->keys, v.x, h) >= 0) return RADIX - 1;
-        return level(h);
+    __device__ __forceinline__ u32 operator()(const ulonglong2& v, u32 pos) const {
+        if (nhot && ((__ldg(&mask[pos >> 5]) >> (pos & 31)) & 1u)) return RADIX - 1;
+        return level(key_hash(v.x));
     }
 };
 
 // counting read of the first pass (the chunk_hist_kernel of tg_segmented.cuh) that also folds the records of hot keys:
-// chunkcount[chunk][d] for d < RADIX-1 = records of the chunk that the pass will move, [RADIX-1] = records folded here
-__global__ void __launch_bounds__(512) hot_hist_kernel(const ulonglong2* __restrict__ in, u32 n, u32 chunk_items, HotLevelDigit fn,
-                                                       int op, u64 ident, HotTable* ht, u32* __restrict__ chunkcount) {
-    constexpr int U = 4;
-    __shared__ u32 sh[RADIX];
-    __shared__ u64 hkeys[HOT_SLOTS];
-    __shared__ u64 hacc[HOT_SLOTS];
+// chunkcount[chunk][d] for d < RADIX-1 = records of the chunk that the pass will move, [RADIX-1] = records folded here (their
+// bits are set in mask).  Hot keys are accumulated in shared memory: the HOT_SUPER most frequent ones in warp-private
+// accumulators (a key with 5 % of the records would otherwise serialise the whole CTA on one shared-memory word), the others in
+// one table per CTA; everything is flushed to the hot table's accumulators at the end.
+constexpr int HOT_HIST_SMEM = HOT_SLOTS * 16 + (HOT_HIST_THREADS / 32) * HOT_SUPER * 8 + HOT_SLOTS + RADIX * 4;
+__global__ void __launch_bounds__(HOT_HIST_THREADS) hot_hist_kernel(const ulonglong2* __restrict__ in, u32 n, u32 chunk_items, HotLevelDigit fn,
+                                                                    int op, u64 ident, HotTable* ht, u32* __restrict__ chunkcount,
+                                                                    u32* __restrict__ mask) {
+    constexpr int U = 4, NW = HOT_HIST_THREADS / 32;
+    extern __shared__ __align__(16) unsigned char hot_smem[];
+    u64* const hhash = reinterpret_cast<u64*>(hot_smem);                    // [HOT_SLOTS]
+    u64* const hacc = hhash + HOT_SLOTS;                                    // [HOT_SLOTS]
+    u64* const wacc = hacc + HOT_SLOTS;                                     // [NW][HOT_SUPER]
+    unsigned char* const hsuper = reinterpret_cast<unsigned char*>(wacc + NW * HOT_SUPER);    // [HOT_SLOTS]
+    u32* const sh = reinterpret_cast<u32*>(hsuper + HOT_SLOTS);             // [RADIX]
     fn.init();
     const bool hot = fn.nhot != 0;
+    const u32 lane = lane_id(), warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < RADIX; i += blockDim.x) sh[i] = 0;
-    if (hot)
-        for (int i = threadIdx.x; i < (int)HOT_SLOTS; i += blockDim.x) { hkeys[i] = ht->keys[i]; hacc[i] = ident; }
+    if (hot) {
+        for (int i = threadIdx.x; i < (int)HOT_SLOTS; i += blockDim.x) { hhash[i] = ht->hashes[i]; hacc[i] = ident; hsuper[i] = ht->super_idx[i]; }
+        for (int i = threadIdx.x; i < NW * (int)HOT_SUPER; i += blockDim.x) wacc[i] = ident;
+    }
     __syncthreads();
     const u32 lo = blockIdx.x * chunk_items;
     const u32 hi = (n - lo < chunk_items) ? n : lo + chunk_items;
@@ -570,12 +606,22 @@ __global__ void __launch_bounds__(512) hot_hist_kernel(const ulonglong2* __restr
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            if (!valid[u]) continue;
-            const u64 h = key_hash(v[u].x);
+            const u32 i = base + u * blockDim.x + threadIdx.x;
             int slot = -1;
-            if (hot && v[u].x != 0) slot = hot_find(hkeys, v[u].x, h);
+            u64 h = 0;
+            if (valid[u]) {
+                h = key_hash(v[u].x);
+                if (hot && v[u].x != 0) slot = hot_find(hhash, h);
+            }
+            if (hot) {
+                const u32 hits = __ballot_sync(0xffffffffu, slot >= 0);
+                const u32 live = __ballot_sync(0xffffffffu, valid[u]);
+                if (lane == 0 && live) mask[i >> 5] = hits;
+            }
+            if (!valid[u]) continue;
             if (slot >= 0) {
-                op_apply(op, &hacc[slot], v[u].y, false);
+                const u32 sj = hsuper[slot];
+                op_apply(op, sj != 0xffu ? &wacc[warp * HOT_SUPER + sj] : &hacc[slot], v[u].y, false);
                 atomicAdd(&sh[RADIX - 1], 1u);
             }
             else atomicAdd(&sh[fn.level(h)], 1u);
@@ -583,9 +629,15 @@ __global__ void __launch_bounds__(512) hot_hist_kernel(const ulonglong2* __restr
     }
     __syncthreads();
     for (int i = threadIdx.x; i < RADIX; i += blockDim.x) chunkcount[(size_t)blockIdx.x * RADIX + i] = sh[i];
-    if (hot)
+    if (hot) {
         for (int i = threadIdx.x; i < (int)HOT_SLOTS; i += blockDim.x)
-            if (hkeys[i] != 0 && hacc[i] != ident) op_apply(op, &ht->acc[i], hacc[i], false);
+            if (hhash[i] != 0 && hacc[i] != ident) op_apply(op, &ht->acc[i], hacc[i], false);
+        if (threadIdx.x < ht->nsuper) {
+            u64 a = ident;
+            for (int w = 0; w < NW; ++w) a = op_combine(op, a, wacc[w * HOT_SUPER + threadIdx.x]);
+            if (a != ident) op_apply(op, &ht->acc[ht->super_slot[threadIdx.x]], a, false);
+        }
+    }
 }
 
 // the hot keys and their folded values appended to the output
@@ -661,18 +713,20 @@ int run_partitioned_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 n, void
     // (0) popular keys: sample, hot table (FIRST keeps the value of one arbitrary record: nothing to fold early)
     const bool use_hot = op != TG_OP_FIRST && !getenv("TG_REDUCE_NO_HOT");
     unsigned char* d_hot;
-    TG_TRY(tg_ws_get(ctx, WS_HOT, sizeof(HotTable) + (size_t)HOT_STAB * 12 + 64, (void**)&d_hot));
+    const size_t hot_fixed = (sizeof(HotTable) + 255) / 256 * 256 + (size_t)HOT_STAB * 12;
+    TG_TRY(tg_ws_get(ctx, WS_HOT, hot_fixed + (n / 32 + 4) * 4 + 64, (void**)&d_hot));
     HotTable* ht = (HotTable*)d_hot;
-    u64* skeys = (u64*)(d_hot + sizeof(HotTable));
+    u64* skeys = (u64*)(d_hot + (sizeof(HotTable) + 255) / 256 * 256);
     u32* scnt = (u32*)(skeys + HOT_STAB);
-    TG_CUDA(ctx, cudaMemsetAsync(d_hot, 0, sizeof(HotTable) + (size_t)HOT_STAB * 12, ctx->stream));
+    u32* hot_mask = scnt + HOT_STAB;                 // one bit per record: folded by the counting read
+    TG_CUDA(ctx, cudaMemsetAsync(d_hot, 0, hot_fixed, ctx->stream));
     if (use_hot) {
         TG_LAUNCH(ctx, hot_sample_kernel, HOT_SAMPLES / 256, 256, 0, (const ulonglong2*)d_in, n, skeys, scnt);
         TG_LAUNCH(ctx, hot_select_kernel, 1, 1024, 0, (const u64*)skeys, (const u32*)scnt, ht, ident);
     }
     // (1) first hash digit: chunked pass; its counting read folds the records of the hot keys, the pass drops them
     u32 *d_tot1, *d_gbase1;
-    HotLevelDigit fn1 = { AGG_SHIFT1, ht, 0 };
+    HotLevelDigit fn1 = { AGG_SHIFT1, ht, hot_mask, 0 };
     {
         const ChunkGeom g = chunk_geometry<2>(ctx, n);
         const size_t cw = (size_t)g.nchunks * RADIX;
@@ -682,7 +736,12 @@ int run_partitioned_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 n, void
         u32* chunkbase = tab + cw;
         d_tot1 = chunkbase + cw;
         d_gbase1 = d_tot1 + RADIX;
-        TG_LAUNCH_T(ctx, TG_K_PREAGG, hot_hist_kernel, g.nchunks, 512, 0, (const ulonglong2*)d_in, (u32)n, g.chunk_items, fn1, op, ident, ht, chunkcount);
+        if (ctx->kernel_cfg.find((const void*)hot_hist_kernel) == ctx->kernel_cfg.end()) {
+            TG_CUDA(ctx, cudaFuncSetAttribute(hot_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HOT_HIST_SMEM));
+            ctx->kernel_cfg[(const void*)hot_hist_kernel] = 2;
+        }
+        TG_LAUNCH_T(ctx, TG_K_PREAGG, hot_hist_kernel, g.nchunks, HOT_HIST_THREADS, HOT_HIST_SMEM, (const ulonglong2*)d_in, (u32)n, g.chunk_items, fn1, op,
+                    ident, ht, chunkcount, hot_mask);
         TG_LAUNCH(ctx, chunk_scan_kernel, 1, 4 * RADIX, 0, chunkcount, g.nchunks, d_tot1, d_gbase1, chunkbase);
         std::vector<u32> chunk_size(g.nchunks, g.chunk_items);
         chunk_size[g.nchunks - 1] = (u32)(n - (size_t)(g.nchunks - 1) * g.chunk_items);
