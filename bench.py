@@ -399,6 +399,64 @@ def bench_sort(args, ctx, world, rank, hbm_peak, peak_src, zipf=False, d_cdf=Non
     return res
 
 
+def bench_terasort(args, ctx, world, rank, hbm_peak, steps=2, warmup=1):
+    """cfg4's per-GPU share: Sort of 100-byte records (10-byte key), device resident; parity = sortedness + multiset + rank
+    boundaries on every rank"""
+    from thrill_b200 import capi
+    tg = ctx.tg
+    L = tg.L
+    n = args.terasort_n
+    desc = capi.record_desc()
+    d_in = tg.alloc(n * 100)
+    ms_list = []
+    for it in range(warmup + steps):
+        tg.ck(L.tg_gen_records(tg.h, d_in, rank * n, n, SEED))
+        if it == warmup:
+            tg.profile_enable(True)
+        if it == warmup + steps - 1:
+            before = tg.checksum(d_in, n, 100)
+        tg.barrier()
+        tg.timer_start()
+        op, on = C.c_void_p(), C.c_size_t()
+        tg.ck(L.tg_sort(tg.h, C.byref(desc), d_in, n, SEED + it, C.byref(op), C.byref(on)))
+        ms = max_over_ranks(tg.timer_stop(), world)
+        if it >= warmup:
+            ms_list.append(ms)
+    gather_ms, gather_cnt = tg.profile_get(capi.K_MERGE)
+    xchg_ms, xchg_cnt = tg.profile_get(capi.K_EXCHANGE)
+    part_ms, part_cnt = tg.profile_get(capi.K_PARTITION)
+    tg.profile_enable(False)
+    ok_sorted = tg.is_sorted(desc, op.value, on.value)
+    after = tg.checksum(op.value, on.value, 100) if on.value else (0, 0)
+    first = bytes(tg.download(op.value, 10)) if on.value else None
+    last = bytes(tg.download(op.value + (on.value - 1) * 100, 10)) if on.value else None
+    allv = gather_objects((before, after, int(on.value), first, last, bool(ok_sorted)), world)
+    m64 = (1 << 64) - 1
+    xb = xa = 0
+    for v in allv:
+        xb ^= v[0][1]; xa ^= v[1][1]
+    total_out = sum(v[2] for v in allv)
+    bounds = [(v[3], v[4]) for v in allv if v[2]]
+    parity = {"sorted_on_every_rank": all(v[5] for v in allv), "items_out": total_out, "items_in": n * world,
+              "multiset_sum_match": (sum(v[0][0] for v in allv) & m64) == (sum(v[1][0] for v in allv) & m64),
+              "multiset_xor_match": xb == xa,
+              "rank_boundaries_ordered": all(bounds[i][1] <= bounds[i + 1][0] for i in range(len(bounds) - 1)),
+              "max_over_mean_items": round(max(v[2] for v in allv) / (float(total_out) / world), 4) if total_out else 1.0}
+    parity["ok"] = bool(parity["sorted_on_every_rank"] and total_out == n * world and parity["multiset_sum_match"]
+                        and parity["multiset_xor_match"] and parity["rank_boundaries_ordered"])
+    tg.free(d_in)
+    step = sum(ms_list) / len(ms_list)
+    model = 668.0 if world == 1 else 1270.0
+    g_launch = gather_ms / max(gather_cnt, 1)
+    return {"records_per_s": n * world / (step / 1e3), "ms_per_step": step, "workload": "terasort_100B_records_10B_key", "records_per_gpu": n,
+            "parity_check": parity,
+            "operator_model": {"bytes_per_record": model, "what": "SURVEY.md 8(d) TeraSort total, p %s 1" % ("=" if world == 1 else ">"),
+                               "achieved_GBps": model * n / (step / 1e3) / 1e9, "frac": model * n / (step / 1e3) / 1e9 / hbm_peak},
+            "gather_kernel": {"kernel": "gather_records_kernel (read 16 B tuple + 100 B record, write 100 B)", "launch_ms": g_launch,
+                              "achieved_GBps": 216.0 * (float(on.value) if world > 1 else n) / (g_launch / 1e3) / 1e9 if g_launch else None},
+            "step_share": {"gather_ms": gather_ms / steps, "tuple_partition_ms": part_ms / steps, "exchange_ms": xchg_ms / steps, "step_ms": step}}
+
+
 def reduce_parity(ctx, world, rank, d_cdf):
     """exact-mode sample (integer-valued doubles: sums are order independent) through the same operator, every key on the
     worker the reference's ReduceByHash puts it on, sums equal to a numpy group-by of the same records"""
@@ -540,6 +598,7 @@ def main():
     ap.add_argument("--metric", default="sort", choices=["sort", "reduce"], help="which operator is the line's metric")
     ap.add_argument("--n", type=int, default=SORT_N_PER_GPU, help="sort keys per GPU")
     ap.add_argument("--reduce-n", type=int, default=REDUCE_N_PER_GPU, help="reduce records per GPU")
+    ap.add_argument("--terasort-n", type=int, default=125000000, help="TeraSort records per GPU of the extra (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="only the metric itself (no second operator, no Zipf sort)")
     args = ap.parse_args()
@@ -575,6 +634,11 @@ def main():
                                    "note": "full line: bench.py --metric reduce"}
             except BaseException as e:          # noqa: BLE001
                 extra["reduce"] = {"error": str(e)[:300]}
+            if args.terasort_n:
+                try:
+                    extra["terasort"] = bench_terasort(args, ctx, world, rank, hbm_peak)
+                except BaseException as e:          # noqa: BLE001
+                    extra["terasort"] = {"error": str(e)[:300]}
         name, unit, dtype, n_item = "sort_keys_per_s", "keys/s", "u64", args.n
     else:
         main_res = bench_reduce(args, ctx, world, rank, hbm_peak, peak_src, d_cdf)

@@ -228,6 +228,30 @@ int tg_reduce_file(tg_ctx* ctx, const tg_kv_desc* desc, const tg_block* in_block
                    size_t* out_items);
 int tg_fetch_output(tg_ctx* ctx, const tg_block_mut* out_blocks, size_t n_out_blocks);
 
+/* ---- device-resident Files: GPU node -> GPU node without the PCIe round trip ----------------------
+ * The reference hands a node's result to its children as a data::File (DIANode::PushFile -> child->OnPreOpFile,
+ * api/dia_node.hpp:156-180; api/sort.hpp:151-175 takes it whole).  When the child is another GPU node the File need not
+ * exist on the host at all: the parent keeps its result as a tg_dev_file (flat items in HBM, the same layout as the
+ * concatenated Blocks) and the child's operator reads it there.  A host File is materialised only when a child that is
+ * not a GPU node asks for it (tg_dev_file_fetch: the lazy D2H of a PinnedBlock, data/block.hpp:116). */
+typedef struct {
+    void* dptr;                /* HBM buffer owned by the handle (tg_dev_file_free) */
+    uint64_t items;
+    uint32_t item_bytes;
+    uint32_t reserved;
+} tg_dev_file;
+/* take the result of the last *_file / *_dev operator as a device File instead of fetching it (tg_fetch_output) */
+int tg_output_detach(tg_ctx* ctx, tg_dev_file* out);
+int tg_dev_file_fetch(tg_ctx* ctx, const tg_dev_file* f, const tg_block_mut* out_blocks, size_t n_out_blocks);
+int tg_dev_file_free(tg_ctx* ctx, tg_dev_file* f);
+/* the operators with a device File as input (the handle is left intact: a DIA may have several children) */
+int tg_sort_dev(tg_ctx* ctx, const tg_key_desc* desc, const tg_dev_file* in, uint64_t rng_seed, size_t* out_items);
+int tg_reduce_dev(tg_ctx* ctx, const tg_kv_desc* desc, const tg_dev_file* in, size_t* out_items);
+int tg_reduce_to_index_dev(tg_ctx* ctx, const tg_kv_desc* desc, const tg_dev_file* in, uint64_t result_size,
+                           const void* neutral_item16, size_t* out_items, uint64_t* out_begin);
+/* bytes this ctx has moved over PCIe through the File codec since tg_init (tests: a GPU -> GPU chain moves none in between) */
+int tg_transfer_bytes(const tg_ctx* ctx, uint64_t* out_h2d, uint64_t* out_d2h);
+
 /* ---- synthetic inputs of SURVEY.md §8(d), generated on the device (bench / tests support) ------------ */
 int tg_gen_sort_uniform(tg_ctx* ctx, void* d_out, uint64_t begin, uint64_t n, uint64_t seed);
 int tg_gen_reduce_uniform(tg_ctx* ctx, void* d_out, uint64_t begin, uint64_t n, uint64_t seed,

@@ -28,6 +28,10 @@ class Block(C.Structure):
     _fields_ = [("data", C.c_void_p), ("bytes", C.c_size_t)]
 
 
+class DevFile(C.Structure):
+    _fields_ = [("dptr", C.c_void_p), ("items", C.c_uint64), ("item_bytes", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 class BlockGeom(C.Structure):
     _fields_ = [("bytes", C.c_uint64), ("first_item", C.c_uint64), ("num_items", C.c_uint64)]
 
@@ -91,6 +95,13 @@ SYMBOLS = [
     ("tg_sort_file", _i, [_vp, _P(KeyDesc), _P(Block), _sz, _u64, _P(_sz)]),
     ("tg_reduce_file", _i, [_vp, _P(KVDesc), _P(Block), _sz, _P(_sz)]),
     ("tg_fetch_output", _i, [_vp, _P(Block), _sz]),
+    ("tg_output_detach", _i, [_vp, _P(DevFile)]),
+    ("tg_dev_file_fetch", _i, [_vp, _P(DevFile), _P(Block), _sz]),
+    ("tg_dev_file_free", _i, [_vp, _P(DevFile)]),
+    ("tg_sort_dev", _i, [_vp, _P(KeyDesc), _P(DevFile), _u64, _P(_sz)]),
+    ("tg_reduce_dev", _i, [_vp, _P(KVDesc), _P(DevFile), _P(_sz)]),
+    ("tg_reduce_to_index_dev", _i, [_vp, _P(KVDesc), _P(DevFile), _u64, _vp, _P(_sz), _P(_u64)]),
+    ("tg_transfer_bytes", _i, [_vp, _P(_u64), _P(_u64)]),
     ("tg_gen_sort_uniform", _i, [_vp, _vp, _u64, _u64, _u64]),
     ("tg_gen_reduce_uniform", _i, [_vp, _vp, _u64, _u64, _u64, _u64, _i]),
     ("tg_gen_sort_zipf", _i, [_vp, _vp, _u64, _u64, _u64, _vp, _u64]),

@@ -263,34 +263,137 @@ int tg_timer_stop(tg_ctx* ctx, float* out_ms) {
 
 int tg_upload(tg_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
     if (bytes) TG_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->bytes_h2d += bytes;
     return TG_OK;
 }
 
 int tg_download(tg_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
     if (bytes) TG_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->bytes_d2h += bytes;
     return TG_OK;
 }
 
+// Blocks that happen to be adjacent in host memory (one arena, a memory-mapped file, ReadBinary's ranges) go as one copy:
+// fewer, longer DMA transfers
 int tg_upload_blocks(tg_ctx* ctx, void* dst_dev, const tg_block* blocks, size_t nblocks, size_t* out_bytes) {
-    size_t off = 0;
-    for (size_t i = 0; i < nblocks; ++i) {
-        if (blocks[i].bytes)
-            TG_CUDA(ctx, cudaMemcpyAsync((char*)dst_dev + off, blocks[i].data, blocks[i].bytes,
-                                         cudaMemcpyHostToDevice, ctx->stream));
-        off += blocks[i].bytes;
+    size_t off = 0, i = 0;
+    while (i < nblocks) {
+        const char* base = (const char*)blocks[i].data;
+        size_t len = blocks[i].bytes, k = i + 1;
+        while (k < nblocks && (blocks[k].bytes == 0 || (const char*)blocks[k].data == base + len)) len += blocks[k++].bytes;
+        if (len) TG_CUDA(ctx, cudaMemcpyAsync((char*)dst_dev + off, base, len, cudaMemcpyHostToDevice, ctx->stream));
+        off += len;
+        i = k;
     }
+    ctx->bytes_h2d += off;
     if (out_bytes) *out_bytes = off;
     return TG_OK;
 }
 
 int tg_download_blocks(tg_ctx* ctx, const void* src_dev, const tg_block_mut* blocks, size_t nblocks) {
-    size_t off = 0;
-    for (size_t i = 0; i < nblocks; ++i) {
-        if (blocks[i].bytes)
-            TG_CUDA(ctx, cudaMemcpyAsync(blocks[i].data, (const char*)src_dev + off, blocks[i].bytes,
-                                         cudaMemcpyDeviceToHost, ctx->stream));
-        off += blocks[i].bytes;
+    size_t off = 0, i = 0;
+    while (i < nblocks) {
+        char* base = (char*)blocks[i].data;
+        size_t len = blocks[i].bytes, k = i + 1;
+        while (k < nblocks && (blocks[k].bytes == 0 || (char*)blocks[k].data == base + len)) len += blocks[k++].bytes;
+        if (len) TG_CUDA(ctx, cudaMemcpyAsync(base, (const char*)src_dev + off, len, cudaMemcpyDeviceToHost, ctx->stream));
+        off += len;
+        i = k;
     }
+    ctx->bytes_d2h += off;
+    return TG_OK;
+}
+
+int tg_transfer_bytes(const tg_ctx* ctx, uint64_t* out_h2d, uint64_t* out_d2h) {
+    if (!ctx) return TG_ERR_ARG;
+    if (out_h2d) *out_h2d = ctx->bytes_h2d;
+    if (out_d2h) *out_d2h = ctx->bytes_d2h;
+    return TG_OK;
+}
+
+// ---- device-resident Files (include/thrill_gpu.h) ----------------------------------------------------------------------
+int tg_output_detach(tg_ctx* ctx, tg_dev_file* out) {
+    if (!ctx || !out) return TG_ERR_ARG;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = ctx->out_items * (size_t)ctx->out_item_bytes;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 256);
+    if (e != cudaSuccess) { cudaGetLastError(); return tg_set_error(ctx, TG_ERR_OOM, "device File: cudaMalloc(%zu) -> %s", bytes, cudaGetErrorString(e)); }
+    // (the result lies in a workspace slot, the exchange window or the operator's input buffer, all of which the next operator
+    // re-uses: one device-to-device copy, ~0.1 ms per GB, makes the File independent of them)
+    if (bytes) TG_CUDA(ctx, cudaMemcpyAsync(p, ctx->out_ptr, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    out->dptr = p; out->items = ctx->out_items; out->item_bytes = ctx->out_item_bytes; out->reserved = 0;
+    ctx->out_ptr = nullptr; ctx->out_items = 0;
+    return TG_OK;
+}
+
+int tg_dev_file_fetch(tg_ctx* ctx, const tg_dev_file* f, const tg_block_mut* out_blocks, size_t n_out_blocks) {
+    if (!ctx || !f) return TG_ERR_ARG;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t bytes = 0;
+    for (size_t i = 0; i < n_out_blocks; ++i) bytes += out_blocks[i].bytes;
+    if (bytes != f->items * (size_t)f->item_bytes)
+        return tg_set_error(ctx, TG_ERR_ARG, "dev_file_fetch: blocks hold %zu bytes, the File has %zu", bytes, (size_t)(f->items * f->item_bytes));
+    if (bytes) TG_TRY(tg_download_blocks(ctx, f->dptr, out_blocks, n_out_blocks));
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TG_OK;
+}
+
+int tg_dev_file_free(tg_ctx* ctx, tg_dev_file* f) {
+    if (!f || !f->dptr) return TG_OK;
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    cudaFree(f->dptr);
+    f->dptr = nullptr; f->items = 0;
+    return TG_OK;
+}
+
+// the operator input of a device File: copied into the ctx's input workspace (operators clobber their input)
+static int stage_dev_file(tg_ctx* ctx, const tg_dev_file* in, uint32_t item_bytes, void** d_in) {
+    if (!in || in->item_bytes != item_bytes) return tg_set_error(ctx, TG_ERR_ARG, "device File: item size %u, operator expects %u", in ? in->item_bytes : 0, item_bytes);
+    const size_t bytes = in->items * (size_t)in->item_bytes;
+    TG_TRY(tg_ws_get(ctx, WS_IN, bytes + 16, d_in));
+    if (bytes) TG_CUDA(ctx, cudaMemcpyAsync(*d_in, in->dptr, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return TG_OK;
+}
+
+int tg_sort_dev(tg_ctx* ctx, const tg_key_desc* desc, const tg_dev_file* in, uint64_t rng_seed, size_t* out_items) {
+    if (!ctx || !desc || !out_items) return TG_ERR_ARG;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    void* d_in;
+    TG_TRY(stage_dev_file(ctx, in, desc->item_bytes, &d_in));
+    void* out = nullptr;
+    size_t n_out = 0;
+    TG_TRY(tg_sort(ctx, desc, d_in, in->items, rng_seed, &out, &n_out));
+    ctx->out_ptr = out; ctx->out_items = n_out; ctx->out_item_bytes = desc->item_bytes;
+    *out_items = n_out;
+    return TG_OK;
+}
+
+int tg_reduce_dev(tg_ctx* ctx, const tg_kv_desc* desc, const tg_dev_file* in, size_t* out_items) {
+    if (!ctx || !desc || !out_items) return TG_ERR_ARG;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    void* d_in;
+    TG_TRY(stage_dev_file(ctx, in, 16, &d_in));
+    void* out = nullptr;
+    size_t n_out = 0;
+    TG_TRY(tg_reduce_by_key(ctx, desc, d_in, in->items, &out, &n_out));
+    ctx->out_ptr = out; ctx->out_items = n_out; ctx->out_item_bytes = 16;
+    *out_items = n_out;
+    return TG_OK;
+}
+
+int tg_reduce_to_index_dev(tg_ctx* ctx, const tg_kv_desc* desc, const tg_dev_file* in, uint64_t result_size,
+                           const void* neutral_item16, size_t* out_items, uint64_t* out_begin) {
+    if (!ctx || !desc || !out_items || !out_begin) return TG_ERR_ARG;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    void* d_in;
+    TG_TRY(stage_dev_file(ctx, in, 16, &d_in));
+    void* out = nullptr;
+    size_t n_out = 0;
+    TG_TRY(tg_reduce_to_index(ctx, desc, d_in, in->items, result_size, neutral_item16, &out, &n_out, out_begin));
+    ctx->out_ptr = out; ctx->out_items = n_out; ctx->out_item_bytes = 16;
+    *out_items = n_out;
     return TG_OK;
 }
 

@@ -292,7 +292,8 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
     __syncthreads();
 
     u32 j = blockIdx.x;
-    TileInfo tnext = tile_info(j < num_tiles ? j : 0);        // descriptor of the tile of the next iteration, fetched one ahead
+    TileInfo tnext = tile_info(j < num_tiles ? j : 0);        // descriptors of the tiles of the next two iterations
+    TileInfo tnext2 = tile_info(j + gridDim.x < num_tiles ? j + gridDim.x : 0);
     if (TMA && j < num_tiles) {
         const TileInfo t0 = tnext;
         if (tid == 0 && tma_ok(t0)) {
@@ -308,7 +309,10 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
         Item* const buf = cur ? buf1 : buf0;
         Item* const nbuf = cur ? buf0 : buf1;
         const TileInfo ti = tnext;
-        if (j + gridDim.x < num_tiles) tnext = tile_info(j + gridDim.x);
+        // (descriptors are fetched two tiles ahead: the one of the next tile, needed right below to start its TMA copy, was
+        // requested a whole tile ago)
+        if (j + gridDim.x < num_tiles) tnext = tnext2;
+        if (SEG ? (j + 2 * gridDim.x < num_tiles) : true) tnext2 = tile_info(j + 2 * gridDim.x);
         const u32 tile_base = ti.start;
         const bool full_tile = ti.len == (u32)TILE;
         const u32 tile_valid = ti.len;

@@ -43,6 +43,20 @@ struct SplitterDigit {
     __device__ __forceinline__ void init() { if (gbase_dev) gbase = *gbase_dev; }
     template <class Item>
     __device__ __forceinline__ u32 operator()(const Item& v, u32 pos) const {
+        if (kv.kind == TG_KEY_UINT_LE && kv.bytes == 8 && (kv.off & 7) == 0) {
+            // integer key in one item word: search on the key alone (8-byte loads), then step over the splitters that tie with it
+            // and precede the item by global index (EqualSampleGreaterIndex, api/sort.hpp:424-426)
+            u64 k = item_word(v, (int)(kv.off >> 3));
+            if (kv.desc) k = ~k;
+            u32 lo = 0, hi = nspl;
+            while (lo < hi) {
+                const u32 mid = (lo + hi) >> 1;
+                if (spl[mid].lo < k) lo = mid + 1; else hi = mid;
+            }
+            const u64 gi = gbase + pos;
+            while (lo < nspl && spl[lo].lo == k && spl[lo].idx < gi) ++lo;
+            return lo;
+        }
         Canon k = canon_key(v, kv);
         CanonIdx me = { k.hi, k.lo, gbase + pos };
         u32 lo = 0, hi = nspl;

@@ -32,6 +32,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <type_traits>
 #include <utility>
 #include <vector>
@@ -238,9 +239,75 @@ inline void FetchIntoFile(tg_ctx* c, Context& ctx, size_t num_items, uint32_t it
 }
 
 /******************************************************************************/
+// GPU node -> GPU node hand-off without the PCIe round trip
+
+//! A node result that lives in HBM (tg_dev_file); shared by the parent and the children it was handed to.
+class DeviceFile
+{
+public:
+    DeviceFile(tg_ctx* c, const tg_dev_file& f) : ctx_(c), f_(f) { }
+    DeviceFile(const DeviceFile&) = delete;
+    DeviceFile& operator = (const DeviceFile&) = delete;
+    ~DeviceFile() { tg_dev_file_free(ctx_, &f_); }
+    const tg_dev_file * get() const { return &f_; }
+    size_t items() const { return f_.items; }
+
+private:
+    tg_ctx* ctx_;
+    tg_dev_file f_;
+};
+using DeviceFilePtr = std::shared_ptr<DeviceFile>;
+
+//! Implemented by the GPU nodes: a parent GPU node offers its device-resident result instead of a data::File.  The offer is
+//! made inside the parent's PushData, i.e. between the child's StartPreOp and StopPreOp, exactly where OnPreOpFile would be
+//! called (api/dia_node.hpp:156-180); a child whose function stack towards this parent is not empty declines.
+class GpuNodeBase
+{
+public:
+    virtual ~GpuNodeBase() { }
+    virtual bool OnPreOpDeviceFile(const DeviceFilePtr& file, size_t item_bytes) = 0;
+};
+
+//! materialise a device File as a host data::File (the lazy D2H, only for children that are not GPU nodes)
+inline void FetchDeviceFileIntoFile(tg_ctx* c, Context& ctx, const DeviceFile& df, uint32_t item_bytes,
+                                    thrill::data::File& out) {
+    size_t num_items = df.items();
+    size_t nblocks = tg_file_geometry(num_items, item_bytes, thrill::data::start_block_size,
+                                      thrill::data::default_block_size, nullptr, 0);
+    std::vector<tg_block_geom> geom(nblocks);
+    tg_file_geometry(num_items, item_bytes, thrill::data::start_block_size,
+                     thrill::data::default_block_size, geom.data(), geom.size());
+    std::vector<thrill::data::PinnedByteBlockPtr> bytes;
+    std::vector<tg_block_mut> targets;
+    bytes.reserve(nblocks);
+    for (const tg_block_geom& g : geom) {
+        size_t cap = thrill::data::start_block_size;
+        while (cap < g.bytes) cap *= 2;
+        bytes.emplace_back(ctx.block_pool().AllocateByteBlock(cap, ctx.local_worker_id()));
+        targets.push_back(tg_block_mut { bytes.back()->data(), static_cast<size_t>(g.bytes) });
+    }
+    Check(c, tg_dev_file_fetch(c, df.get(), targets.data(), targets.size()), "tg_dev_file_fetch");
+    for (size_t i = 0; i < nblocks; ++i) {
+        thrill::data::PinnedBlock pb(std::move(bytes[i]), 0, geom[i].bytes, geom[i].first_item,
+                                     geom[i].num_items, /* typecode_verify */ false);
+        out.AppendBlock(std::move(pb).MoveToBlock());
+    }
+}
+
+//! true if every child of `node` is a GPU node (so no host File is needed)
+template <typename Node>
+bool AllChildrenAreGpuNodes(const Node& node) {
+    std::vector<thrill::api::DIABase*> ch = node.children();
+    if (ch.empty()) return false;
+    for (thrill::api::DIABase* c : ch)
+        if (dynamic_cast<GpuNodeBase*>(c) == nullptr) return false;
+    return true;
+}
+
+/******************************************************************************/
 
 template <typename ValueType>
-class GpuSortNode final : public thrill::api::DOpNode<ValueType>
+class GpuSortNode final : public thrill::api::DOpNode<ValueType>, public GpuNodeBase
 {
     using Super = thrill::api::DOpNode<ValueType>;
     using Super::context_;
@@ -265,28 +332,55 @@ public:
         return true;
     }
 
+    //! a parent GPU node hands its result over in HBM
+    bool OnPreOpDeviceFile(const DeviceFilePtr& file, size_t item_bytes) final {
+        if (!parent_stack_empty_ || item_bytes != sizeof(ValueType)) return false;
+        device_input_ = file;
+        return true;
+    }
+
     void StopPreOp(size_t /* parent_index */) final { unsorted_writer_.Close(); }
 
     DIAMemUse ExecuteMemUse() final { return DIAMemUse::Max(); }
 
-    //! MainOp (api/sort.hpp:537-663) + the local sort / merge, all behind tg_sort_file.  Collective.
+    //! MainOp (api/sort.hpp:537-663) + the local sort, all behind tg_sort_file / tg_sort_dev.  Collective.  The result stays
+    //! in HBM; PushData hands it to GPU children as it is and writes a host File only if another kind of child needs one.
     void Execute() final {
         tg_ctx* c = WorkerCtx(context_);
         size_t out_items = 0;
-        {
+        if (device_input_) {
+            Check(c, tg_sort_dev(c, &desc_, device_input_->get(), context_.rng_(), &out_items), "tg_sort_dev");
+            device_input_.reset();
+        }
+        else {
             PinnedFileView view(unsorted_file_, context_.local_worker_id());
             Check(c, tg_sort_file(c, &desc_, view.data(), view.size(), context_.rng_(), &out_items), "tg_sort_file");
         }
         unsorted_file_.Clear();
-        FetchIntoFile(c, context_, out_items, sizeof(ValueType), sorted_file_);
+        tg_dev_file f;
+        Check(c, tg_output_detach(c, &f), "tg_output_detach");
+        device_result_ = std::make_shared<DeviceFile>(c, f);
+        have_host_file_ = false;
     }
 
     DIAMemUse PushDataMemUse() final { return 0; }
 
     //! one sorted run per worker: always the files_.size() == 1 branch of SortNode::PushData (:224-227)
-    void PushData(bool consume) final { this->PushFile(sorted_file_, consume); }
+    void PushData(bool consume) final {
+        if (device_result_ && AllChildrenAreGpuNodes(*this)) {
+            bool all = true;
+            for (thrill::api::DIABase* ch : this->children())
+                all = dynamic_cast<GpuNodeBase*>(ch)->OnPreOpDeviceFile(device_result_, sizeof(ValueType)) && all;
+            if (all) return;
+        }
+        if (!have_host_file_) {
+            FetchDeviceFileIntoFile(WorkerCtx(context_), context_, *device_result_, sizeof(ValueType), sorted_file_);
+            have_host_file_ = true;
+        }
+        this->PushFile(sorted_file_, consume);
+    }
 
-    void Dispose() final { sorted_file_.Clear(); }
+    void Dispose() final { sorted_file_.Clear(); device_result_.reset(); have_host_file_ = false; }
 
 private:
     tg_key_desc desc_;
@@ -294,10 +388,12 @@ private:
     thrill::data::File unsorted_file_ { context_.GetFile(this) };
     thrill::data::File::Writer unsorted_writer_;
     thrill::data::File sorted_file_ { context_.GetFile(this) };
+    DeviceFilePtr device_input_, device_result_;
+    bool have_host_file_ = false;
 };
 
 template <typename ValueType>
-class GpuReduceNode final : public thrill::api::DOpNode<ValueType>
+class GpuReduceNode final : public thrill::api::DOpNode<ValueType>, public GpuNodeBase
 {
     using Super = thrill::api::DOpNode<ValueType>;
     using Super::context_;
@@ -332,33 +428,62 @@ public:
         return true;
     }
 
-    //! pre phase flush + exchange + post phase (api/reduce_by_key.hpp:157-211) behind tg_reduce_file.  Collective.
+    bool OnPreOpDeviceFile(const DeviceFilePtr& file, size_t item_bytes) final {
+        if (!parent_stack_empty_ || item_bytes != sizeof(ValueType)) return false;
+        device_input_ = file;
+        return true;
+    }
+
+    //! pre phase flush + exchange + post phase (api/reduce_by_key.hpp:157-211) behind tg_reduce_file / tg_reduce_dev.
+    //! Collective.  The result stays in HBM until PushData knows who wants it.
     void StopPreOp(size_t /* parent_index */) final {
         input_writer_.Close();
         tg_ctx* c = WorkerCtx(context_);
         size_t out_items = 0;
-        {
+        static_assert(sizeof(ValueType) == 16, "16-byte (key, value) items");
+        uint64_t begin = 0;
+        if (device_input_) {
+            if (to_index_)
+                Check(c, tg_reduce_to_index_dev(c, &desc_, device_input_->get(), result_size_, &neutral_, &out_items, &begin),
+                      "tg_reduce_to_index_dev");
+            else
+                Check(c, tg_reduce_dev(c, &desc_, device_input_->get(), &out_items), "tg_reduce_dev");
+            device_input_.reset();
+        }
+        else {
             PinnedFileView view(input_file_, context_.local_worker_id());
-            if (to_index_) {
-                static_assert(sizeof(ValueType) == 16, "16-byte (index, value) items");
-                uint64_t begin = 0;
+            if (to_index_)
                 Check(c, tg_reduce_to_index_file(c, &desc_, view.data(), view.size(), result_size_, &neutral_, &out_items, &begin),
                       "tg_reduce_to_index_file");
-            }
             else
                 Check(c, tg_reduce_file(c, &desc_, view.data(), view.size(), &out_items), "tg_reduce_file");
         }
         input_file_.Clear();
-        FetchIntoFile(c, context_, out_items, sizeof(ValueType), reduced_file_);
+        tg_dev_file f;
+        Check(c, tg_output_detach(c, &f), "tg_output_detach");
+        device_result_ = std::make_shared<DeviceFile>(c, f);
+        have_host_file_ = false;
     }
 
     void Execute() final { }
 
     DIAMemUse PushDataMemUse() final { return 0; }
 
-    void PushData(bool consume) final { this->PushFile(reduced_file_, consume); }
+    void PushData(bool consume) final {
+        if (device_result_ && AllChildrenAreGpuNodes(*this)) {
+            bool all = true;
+            for (thrill::api::DIABase* ch : this->children())
+                all = dynamic_cast<GpuNodeBase*>(ch)->OnPreOpDeviceFile(device_result_, sizeof(ValueType)) && all;
+            if (all) return;
+        }
+        if (!have_host_file_) {
+            FetchDeviceFileIntoFile(WorkerCtx(context_), context_, *device_result_, sizeof(ValueType), reduced_file_);
+            have_host_file_ = true;
+        }
+        this->PushFile(reduced_file_, consume);
+    }
 
-    void Dispose() final { reduced_file_.Clear(); }
+    void Dispose() final { reduced_file_.Clear(); device_result_.reset(); have_host_file_ = false; }
 
 private:
     tg_kv_desc desc_;
@@ -369,6 +494,8 @@ private:
     thrill::data::File input_file_ { context_.GetFile(this) };
     thrill::data::File::Writer input_writer_;
     thrill::data::File reduced_file_ { context_.GetFile(this) };
+    DeviceFilePtr device_input_, device_result_;
+    bool have_host_file_ = false;
 };
 
 /******************************************************************************/
