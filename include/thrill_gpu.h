@@ -231,8 +231,8 @@ int tg_fetch_output(tg_ctx* ctx, const tg_block_mut* out_blocks, size_t n_out_bl
 /* ---- device-resident Files: GPU node -> GPU node without the PCIe round trip ----------------------
  * The reference hands a node's result to its children as a data::File (DIANode::PushFile -> child->OnPreOpFile,
  * api/dia_node.hpp:156-180; api/sort.hpp:151-175 takes it whole).  When the child is another GPU node the File need not
- * exist on the host at all: the parent keeps its result as a tg_dev_file (flat items in HBM, the same layout as the
- * concatenated Blocks) and the child's operator reads it there.  A host File is materialised only when a child that is
+ * exist on the host at all: the parent keeps its result as a device File: flat items in HBM, the same layout as the
+ * concatenated Blocks, and the child's operator reads it there.  A host File is materialised only when a child that is
  * not a GPU node asks for it (tg_dev_file_fetch: the lazy D2H of a PinnedBlock, data/block.hpp:116). */
 typedef struct {
     void* dptr;                /* HBM buffer owned by the handle (tg_dev_file_free) */
