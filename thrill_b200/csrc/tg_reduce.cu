@@ -261,7 +261,7 @@ constexpr u32 AGG_FLUSH_FILL = AGG_SLOTS * 3 / 4;  // the table is emitted early
 template <int OP>
 __global__ void __launch_bounds__(AGG_THREADS, 3)
 agg_units_kernel(const ulonglong2* __restrict__ in, const uint2* __restrict__ units /* {first record, records | long << 30 | partial << 31} */,
-                 u32* __restrict__ nunits_ptr, u64 ident, ulonglong2* __restrict__ out, u64* __restrict__ cursor,
+                 u32 max_units, u32* __restrict__ nunits_ptr /* build_units_kernel's counters */, u64 ident, ulonglong2* __restrict__ out, u64* __restrict__ cursor,
                  ulonglong2* __restrict__ dup_out, u64* __restrict__ dup_cursor, u64* __restrict__ zero_slot) {
     extern __shared__ __align__(16) unsigned char agg_smem[];
     u64* const keys = reinterpret_cast<u64*>(agg_smem);
@@ -274,8 +274,9 @@ agg_units_kernel(const ulonglong2* __restrict__ in, const uint2* __restrict__ un
     const u32 lane = lane_id(), warp = threadIdx.x >> 5;
     constexpr int op = OP;             // compile-time: the reduce function's switch folds away
     constexpr int EI = AGG_SLOTS / AGG_THREADS;
-    const u32 nunits = nunits_ptr[0];
-    u32* const work = nunits_ptr + 1;           // dynamic scheduling: the long units are at the front of the list
+    const u32 nbig = nunits_ptr[0], nunits = nbig + nunits_ptr[2];
+    u32* const work = nunits_ptr + 1;           // dynamic scheduling: work ids below nbig are the long units
+    auto unit_at = [&](u32 w) -> uint2 { return __ldg(&units[w < nbig ? w : max_units - 1 - (w - nbig)]); };
 
     // Thread 0 fetches the id and the descriptor of a unit into next_unit[b] in three steps spread over the work of the
     // unit before it, so that neither L2 round trip (the work counter, the descriptor) is waited for: fetch_id at the start
@@ -285,7 +286,7 @@ agg_units_kernel(const ulonglong2* __restrict__ in, const uint2* __restrict__ un
     uint2 pend_desc = make_uint2(0, 0);
     int pend_buf = -1;
     auto fetch_id = [&](int b) { pend_id = atomicAdd(work, 1u); pend_buf = b; };
-    auto fetch_desc = [&]() { if (pend_buf >= 0) pend_desc = pend_id < nunits ? __ldg(&units[pend_id]) : make_uint2(0, 0); };
+    auto fetch_desc = [&]() { if (pend_buf >= 0) pend_desc = pend_id < nunits ? unit_at(pend_id) : make_uint2(0, 0); };
     auto fetch_store = [&]() {
         if (pend_buf >= 0) { next_unit[pend_buf] = make_uint4(pend_id, pend_desc.x, pend_desc.y, 0); pend_buf = -1; }
     };
@@ -551,32 +552,30 @@ __global__ void __launch_bounds__(1024) hot_select_kernel(const u64* __restrict_
     }
 }
 
-// digit of the first pass (values 0..254 of the hash byte, rescaled) or RADIX-1 = a record of a hot key, which the counting
-// read has folded and marked in `mask` (one bit per record): dropped
+// digit of the first pass: values 0..254 of the hash byte (rescaled), or RADIX-1 = a record of a hot key, which the counting
+// read has folded: dropped.  The counting read leaves every record's digit in `dig` (one byte per record: 0.8 % of the pass's
+// traffic), so the pass itself neither hashes nor probes.
 struct HotLevelDigit {
     int shift;
     const HotTable* ht;
-    const u32* mask;
+    const unsigned char* dig;
     u32 nhot;
     static constexpr bool kStoreDigit = true;
     static constexpr bool kHasDrop = true;
     __device__ __forceinline__ void init() { nhot = ht->nhot; }
     __device__ __forceinline__ u32 level(u64 h) const { return (((u32)(h >> shift) & (RADIX - 1)) * (RADIX - 1)) >> RADIX_BITS; }
-    __device__ __forceinline__ u32 operator()(const ulonglong2& v, u32 pos) const {
-        if (nhot && ((__ldg(&mask[pos >> 5]) >> (pos & 31)) & 1u)) return RADIX - 1;
-        return level(key_hash(v.x));
-    }
+    __device__ __forceinline__ u32 operator()(const ulonglong2&, u32 pos) const { return __ldg(&dig[pos]); }
 };
 
 // counting read of the first pass (the chunk_hist_kernel of tg_segmented.cuh) that also folds the records of hot keys:
-// chunkcount[chunk][d] for d < RADIX-1 = records of the chunk that the pass will move, [RADIX-1] = records folded here (their
-// bits are set in mask).  Hot keys are accumulated in shared memory: the HOT_SUPER most frequent ones in warp-private
+// chunkcount[chunk][d] for d < RADIX-1 = records of the chunk that the pass will move, [RADIX-1] = records folded here; every
+// record's digit goes to dig[].  Hot keys are accumulated in shared memory: the HOT_SUPER most frequent ones in warp-private
 // accumulators (a key with 5 % of the records would otherwise serialise the whole CTA on one shared-memory word), the others in
 // one table per CTA; everything is flushed to the hot table's accumulators at the end.
 constexpr int HOT_HIST_SMEM = HOT_SLOTS * 16 + (HOT_HIST_THREADS / 32) * HOT_SUPER * 8 + HOT_SLOTS + RADIX * 4;
 __global__ void __launch_bounds__(HOT_HIST_THREADS) hot_hist_kernel(const ulonglong2* __restrict__ in, u32 n, u32 chunk_items, HotLevelDigit fn,
                                                                     int op, u64 ident, HotTable* ht, u32* __restrict__ chunkcount,
-                                                                    u32* __restrict__ mask) {
+                                                                    unsigned char* __restrict__ dig) {
     constexpr int U = 4, NW = HOT_HIST_THREADS / 32;
     extern __shared__ __align__(16) unsigned char hot_smem[];
     u64* const hhash = reinterpret_cast<u64*>(hot_smem);                    // [HOT_SLOTS]
@@ -586,7 +585,7 @@ __global__ void __launch_bounds__(HOT_HIST_THREADS) hot_hist_kernel(const ulongl
     u32* const sh = reinterpret_cast<u32*>(hsuper + HOT_SLOTS);             // [RADIX]
     fn.init();
     const bool hot = fn.nhot != 0;
-    const u32 lane = lane_id(), warp = threadIdx.x >> 5;
+    const u32 warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < RADIX; i += blockDim.x) sh[i] = 0;
     if (hot) {
         for (int i = threadIdx.x; i < (int)HOT_SLOTS; i += blockDim.x) { hhash[i] = ht->hashes[i]; hacc[i] = ident; hsuper[i] = ht->super_idx[i]; }
@@ -613,18 +612,14 @@ __global__ void __launch_bounds__(HOT_HIST_THREADS) hot_hist_kernel(const ulongl
                 h = key_hash(v[u].x);
                 if (hot && v[u].x != 0) slot = hot_find(hhash, h);
             }
-            if (hot) {
-                const u32 hits = __ballot_sync(0xffffffffu, slot >= 0);
-                const u32 live = __ballot_sync(0xffffffffu, valid[u]);
-                if (lane == 0 && live) mask[i >> 5] = hits;
-            }
             if (!valid[u]) continue;
+            const u32 d = slot >= 0 ? (u32)(RADIX - 1) : fn.level(h);
+            dig[i] = (unsigned char)d;
             if (slot >= 0) {
                 const u32 sj = hsuper[slot];
                 op_apply(op, sj != 0xffu ? &wacc[warp * HOT_SUPER + sj] : &hacc[slot], v[u].y, false);
-                atomicAdd(&sh[RADIX - 1], 1u);
             }
-            else atomicAdd(&sh[fn.level(h)], 1u);
+            atomicAdd(&sh[d], 1u);
         }
     }
     __syncthreads();
@@ -648,55 +643,29 @@ __global__ void __launch_bounds__(1024) hot_emit_kernel(const HotTable* ht, ulon
     }
 }
 
-// Units straight from the segment table (the segments lie back to back in table order): 2^group_log2 consecutive segments
-// form a unit; a unit of more than AGG_UNIT records is streamed in rounds with the intra-warp reduction switched on
-// (dominated by popular keys), one of more than AGG_MAX_UNIT records is cut into partial pieces.  One CTA of 1024 threads.
-__global__ void __launch_bounds__(1024) build_units_kernel(const u32* __restrict__ segcount, int nseg, int group_log2,
-                                                            uint2* __restrict__ units, u32* __restrict__ nunits_out /* [0] = units, [1] = work counter */) {
-    __shared__ u32 wrec[32], wbig[32], wsml[32];
-    __shared__ u32 total_big;
+// Units straight from the segment tables (the segments lie back to back in table order; segstart[s] = position of segment s):
+// 2^group_log2 consecutive segments form a unit; a unit of more than AGG_UNIT records is streamed in rounds with the intra-warp
+// reduction switched on (dominated by popular keys), one of more than AGG_MAX_UNIT records is cut into partial pieces.  The
+// long units are listed from the front of `units` (they are scheduled first), the short ones from its back; one thread per
+// group, positions by atomic counters: ctr[0] = long entries, ctr[1] = work counter of the aggregation, ctr[2] = short entries.
+__global__ void __launch_bounds__(256) build_units_kernel(const u32* __restrict__ segcount, const u32* __restrict__ segstart, int nseg,
+                                                           int group_log2, uint2* __restrict__ units, u32 max_units, u32* __restrict__ ctr) {
     const int ngroups = nseg >> group_log2, gsz = 1 << group_log2;
-    const int per = (ngroups + 1023) / 1024;
-    const int g0 = threadIdx.x * per, g1 = (g0 + per < ngroups) ? g0 + per : ngroups;
-    // long units (streamed in several rounds) go to the front of the list so that the dynamic scheduling starts them first
-    u32 rec = 0, big = 0, sml = 0;
-    for (int g = g0; g < g1; ++g) {
-        u32 len = 0;
-        for (int i = 0; i < gsz; ++i) len += segcount[(size_t)g * gsz + i];
-        rec += len;
-        if (len > (u32)AGG_UNIT) big += (len + AGG_MAX_UNIT - 1) / AGG_MAX_UNIT;
-        else if (len) sml += 1;
-    }
-    const u32 lane = lane_id(), warp = threadIdx.x >> 5;
-    u32 irec = rec, ibig = big, isml = sml;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        u32 a = __shfl_up_sync(0xffffffffu, irec, o), b = __shfl_up_sync(0xffffffffu, ibig, o), c = __shfl_up_sync(0xffffffffu, isml, o);
-        if (lane >= (u32)o) { irec += a; ibig += b; isml += c; }
-    }
-    if (lane == 31) { wrec[warp] = irec; wbig[warp] = ibig; wsml[warp] = isml; }
-    __syncthreads();
-    u32 pos = irec - rec, bpos = ibig - big, spos = isml - sml;
-    for (u32 w = 0; w < warp; ++w) { pos += wrec[w]; bpos += wbig[w]; spos += wsml[w]; }
-    if (threadIdx.x == 1023) {
-        total_big = bpos + big;
-        nunits_out[0] = bpos + big + spos + sml;
-        nunits_out[1] = 0;
-    }
-    __syncthreads();
-    spos += total_big;
-    for (int g = g0; g < g1; ++g) {
-        u32 len = 0;
-        for (int i = 0; i < gsz; ++i) len += segcount[(size_t)g * gsz + i];
-        if (len == 0) continue;
-        if (len <= (u32)AGG_UNIT) units[spos++] = make_uint2(pos, len);
-        else if (len <= AGG_MAX_UNIT) units[bpos++] = make_uint2(pos, len | 0x40000000u);
-        else
-            for (u32 off = 0; off < len; off += AGG_MAX_UNIT) {
-                const u32 l = len - off < AGG_MAX_UNIT ? len - off : AGG_MAX_UNIT;
-                units[bpos++] = make_uint2(pos + off, l | 0xC0000000u);
-            }
-        pos += len;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngroups) return;
+    u32 len = 0;
+    for (int i = 0; i < gsz; ++i) len += segcount[(size_t)g * gsz + i];
+    if (len == 0) return;
+    const u32 pos = segstart[(size_t)g * gsz];
+    if (len <= (u32)AGG_UNIT) units[max_units - 1 - atomicAdd(&ctr[2], 1u)] = make_uint2(pos, len);
+    else if (len <= AGG_MAX_UNIT) units[atomicAdd(&ctr[0], 1u)] = make_uint2(pos, len | 0x40000000u);
+    else {
+        const u32 pieces = (len + AGG_MAX_UNIT - 1) / AGG_MAX_UNIT;
+        u32 at = atomicAdd(&ctr[0], pieces);
+        for (u32 off = 0; off < len; off += AGG_MAX_UNIT) {
+            const u32 l = len - off < AGG_MAX_UNIT ? len - off : AGG_MAX_UNIT;
+            units[at++] = make_uint2(pos + off, l | 0xC0000000u);
+        }
     }
 }
 
@@ -714,11 +683,11 @@ int run_partitioned_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 n, void
     const bool use_hot = op != TG_OP_FIRST && !getenv("TG_REDUCE_NO_HOT");
     unsigned char* d_hot;
     const size_t hot_fixed = (sizeof(HotTable) + 255) / 256 * 256 + (size_t)HOT_STAB * 12;
-    TG_TRY(tg_ws_get(ctx, WS_HOT, hot_fixed + (n / 32 + 4) * 4 + 64, (void**)&d_hot));
+    TG_TRY(tg_ws_get(ctx, WS_HOT, hot_fixed + n + 64, (void**)&d_hot));
     HotTable* ht = (HotTable*)d_hot;
     u64* skeys = (u64*)(d_hot + (sizeof(HotTable) + 255) / 256 * 256);
     u32* scnt = (u32*)(skeys + HOT_STAB);
-    u32* hot_mask = scnt + HOT_STAB;                 // one bit per record: folded by the counting read
+    unsigned char* hot_dig = (unsigned char*)(scnt + HOT_STAB);      // one byte per record: its first-pass digit (RADIX-1: folded)
     TG_CUDA(ctx, cudaMemsetAsync(d_hot, 0, hot_fixed, ctx->stream));
     if (use_hot) {
         TG_LAUNCH(ctx, hot_sample_kernel, HOT_SAMPLES / 256, 256, 0, (const ulonglong2*)d_in, n, skeys, scnt);
@@ -726,7 +695,7 @@ int run_partitioned_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 n, void
     }
     // (1) first hash digit: chunked pass; its counting read folds the records of the hot keys, the pass drops them
     u32 *d_tot1, *d_gbase1;
-    HotLevelDigit fn1 = { AGG_SHIFT1, ht, hot_mask, 0 };
+    HotLevelDigit fn1 = { AGG_SHIFT1, ht, hot_dig, 0 };
     {
         const ChunkGeom g = chunk_geometry<2>(ctx, n);
         const size_t cw = (size_t)g.nchunks * RADIX;
@@ -741,7 +710,7 @@ int run_partitioned_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 n, void
             ctx->kernel_cfg[(const void*)hot_hist_kernel] = 2;
         }
         TG_LAUNCH_T(ctx, TG_K_PREAGG, hot_hist_kernel, g.nchunks, HOT_HIST_THREADS, HOT_HIST_SMEM, (const ulonglong2*)d_in, (u32)n, g.chunk_items, fn1, op,
-                    ident, ht, chunkcount, hot_mask);
+                    ident, ht, chunkcount, hot_dig);
         TG_LAUNCH(ctx, chunk_scan_kernel, 1, 4 * RADIX, 0, chunkcount, g.nchunks, d_tot1, d_gbase1, chunkbase);
         std::vector<u32> chunk_size(g.nchunks, g.chunk_items);
         chunk_size[g.nchunks - 1] = (u32)(n - (size_t)(g.nchunks - 1) * g.chunk_items);
@@ -787,7 +756,9 @@ int run_partitioned_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 n, void
     uint2* d_units;
     TG_TRY(tg_ws_get(ctx, WS_SEG_TILES2, max_units * sizeof(uint2) + 64, (void**)&d_units));
     u32* d_nunits = (u32*)(d_units + max_units);
-    TG_LAUNCH(ctx, build_units_kernel, 1, 1024, 0, segcount, RADIX * RADIX, group_log2, d_units, d_nunits);
+    TG_CUDA(ctx, cudaMemsetAsync(d_nunits, 0, 16, ctx->stream));
+    TG_LAUNCH(ctx, build_units_kernel, ((int)(table_words >> group_log2) + 255) / 256, 256, 0, segcount, (const u32*)segbase, RADIX * RADIX, group_log2,
+              d_units, (u32)max_units, d_nunits);
     ReduceScratch sc;
     TG_TRY(get_scratch(ctx, op, &sc));
     u64* dup_cursor = sc.cursor + 1;
@@ -802,7 +773,7 @@ int run_partitioned_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 n, void
             ctx->kernel_cfg[(const void*)kern] = 3;                                                                     \
         }                                                                                                               \
         TG_LAUNCH_T(ctx, TG_K_AGGREGATE, kern, agrid, AGG_THREADS, AGG_SMEM, (const ulonglong2*)bufB, (const uint2*)d_units, \
-                    d_nunits, ident, (ulonglong2*)d_out, sc.cursor, d_dup, dup_cursor, sc.zero_slot);                     \
+                    (u32)max_units, d_nunits, ident, (ulonglong2*)d_out, sc.cursor, d_dup, dup_cursor, sc.zero_slot);                     \
         break;                                                                                                          \
     }
     switch (op) {

@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(512) seg_count_kernel(const typename ItemT<WOR
 #pragma unroll
     for (int p = 0; p < NPOS; ++p) dl.fn[p].init();
     __shared__ u32 sh[NPOS * RADIX];
-    constexpr int U = 32 / (4 * WORDS);      // 64 bytes of loads in flight per thread
+    constexpr int U = 4;
     for (u32 j = blockIdx.x; j < sl.num_tiles; j += gridDim.x) {
         const uint4 t = __ldg(&sl.tiles[j]);
         for (int i = threadIdx.x; i < NPOS * RADIX; i += blockDim.x) sh[i] = 0;
