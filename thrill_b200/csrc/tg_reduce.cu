@@ -368,6 +368,7 @@ agg_units_kernel(const ulonglong2* __restrict__ in, const uint2* __restrict__ un
             for (int r = 0; r < AGG_RPT; ++r) {
                 u64 v = val[r];
                 bool mine = valid[r];
+                if (!__any_sync(0xffffffffu, mine)) continue;          // (a unit rarely fills all rows: skip the empty ones)
                 const u32 home = (u32)(key_hash(key[r]) >> AGG_SHIFT_SLOT) & (AGG_SLOTS - 1);
                 // Lanes of the warp that carry the same key are reduced in registers first and one lane touches the table:
                 // records of a popular key sit next to each other here (their segment holds little else), and several lanes on
