@@ -40,9 +40,10 @@ typedef enum {
 /* ---- descriptors: the closed set of (type, functor) pairs the GPU path accepts ----------------------
  * Reference operators take arbitrary C++ lambdas (api/dia.hpp:1753-1816 Sort(cmp), :929-1170
  * ReduceByKey(key_ex, red_fn)).  The host shim recognises the supported functor types and fills these. */
-enum { TG_KEY_UINT_LE = 0,     /* unsigned little-endian integer key, key_bytes in {4,8}: std::less<T> */
+enum { TG_KEY_UINT_LE = 0,     /* unsigned little-endian integer key of 1..8 bytes inside 8- or 16-byte items: std::less<T> */
        TG_KEY_BYTES_BE = 1 };  /* byte-string key compared lexicographically (TeraSort Record,
-                                  examples/terasort/terasort.cpp:35-37), key_bytes <= 16 */
+                                  examples/terasort/terasort.cpp:35-37): <= 16 bytes in 16-byte items, <= 12 bytes in
+                                  records (item_bytes % 4 == 0, e.g. 100) */
 typedef struct {
     uint32_t item_bytes;       /* serialized item size (data/serialization.hpp:34-49): 8, 16 or 100 */
     uint32_t key_offset;
@@ -194,9 +195,12 @@ int tg_hash_partition(tg_ctx* ctx, const tg_kv_desc* desc, const void* d_in, siz
 
 /* Whole SortNode::MainOp + PushData (api/sort.hpp:537-663, :216-271) on device-resident items:
  * ExPrefixSumTotal (:541) -> samples -> splitters -> classify/scatter -> NCCL Alltoallv (replaces the
- * MixStream exchange :615-641) -> local radix sort / merge of the received runs.  d_in holds n_local items
- * (it is clobbered); *out_dptr is a ctx-owned buffer with *out_n items, valid until the next operator call
- * on this ctx or tg_free(*out_dptr).  Collective. */
+ * MixStream exchange :615-641: here the classification pass stores into the peers' exchange windows) -> local radix sort
+ * of what was received.  d_in holds n_local items (it is clobbered); *out_dptr points to *out_n items inside a ctx-owned
+ * workspace, the exchange window or d_in itself: valid until the next operator call on this ctx, never to be freed by the
+ * caller (tg_free rejects it), to be copied (or detached with tg_output_detach after a *_file / *_dev call) before it is
+ * fed to another operator.  Limits: n_local < 2^30, at most 16 ranks.  Collective: sizes are agreed on by all ranks,
+ * TG_ERR_TOO_LARGE is returned by every rank or by none. */
 int tg_sort(tg_ctx* ctx, const tg_key_desc* desc, void* d_in, size_t n_local, uint64_t rng_seed,
             void** out_dptr, size_t* out_n);
 
