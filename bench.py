@@ -657,6 +657,11 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # bounded sample: the sort baseline runs the full 1e8 keys (~0.7 s per iteration), the reduce baseline 2.5e7 records
         cpu = cpu_baseline(args.metric, n_item if args.metric == "sort" else min(n_item, 25000000))
+        if args.metric == "sort" and isinstance(extra.get("reduce"), dict) and "records_per_s" in extra["reduce"]:
+            try:        # the second operator's reference throughput on the same box (bounded sample), so both ratios are in one line
+                extra["reduce"]["cpu_baseline"] = cpu_baseline("reduce", min(args.reduce_n, 25000000))
+            except BaseException as e:          # noqa: BLE001
+                extra["reduce"]["cpu_baseline"] = {"error": str(e)[:200]}
 
     if rank == 0:
         cfg = workload_config(args.metric, n_item, world)

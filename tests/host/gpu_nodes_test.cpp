@@ -11,14 +11,17 @@
  ******************************************************************************/
 #include <thrill/api/all_gather.hpp>
 #include <thrill/api/cache.hpp>
+#include <thrill/api/collapse.hpp>
 #include <thrill/api/generate.hpp>
 #include <thrill/api/reduce_by_key.hpp>
 #include <thrill/api/reduce_to_index.hpp>
 #include <thrill/api/size.hpp>
 #include <thrill/api/sort.hpp>
+#include <thrill/api/zip.hpp>
 #include <thrill/common/stats_timer.hpp>
 
 #include <algorithm>
+#include <cmath>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -39,6 +42,45 @@ static inline uint64_t splitmix64(uint64_t x) {
 }
 
 static std::atomic<int> g_failures { 0 };
+
+//! PageRank as in examples/page_rank/page_rank.hpp:70-139 (cfg5's pipeline: Zip + FlatMap on the reference's CPU operators,
+//! the ReduceToIndex step either the stock one or the GPU node); returns the gathered ranks
+template <bool UseGpu>
+static std::vector<double> PageRankRun(api::Context& ctx, size_t num_pages, size_t iterations) {
+    using PageId = uint64_t;
+    using OutgoingLinks = std::vector<PageId>;
+    using OutgoingLinksRank = std::pair<OutgoingLinks, double>;
+    using Contrib = std::pair<PageId, double>;
+    const double n_d = static_cast<double>(num_pages);
+    auto links = api::Generate(ctx, num_pages, [num_pages](size_t i) {
+                                   OutgoingLinks ol;
+                                   size_t deg = (i % 17 == 0) ? 0 : 1 + splitmix64(i) % 8;       // some pages have no out-links
+                                   for (size_t j = 0; j < deg; ++j) {
+                                       uint64_t r = splitmix64(i * 16 + j + 1);
+                                       ol.push_back((r % 4 == 0) ? r % 64 : r % num_pages);      // a few popular pages
+                                   }
+                                   return ol;
+                               }).Cache();
+    api::DIA<double> ranks = api::Generate(ctx, num_pages, [n_d](size_t) { return 1.0 / n_d; }).Collapse();
+    for (size_t iter = 0; iter < iterations; ++iter) {
+        auto outs_rank = links.Zip(ranks, [](const OutgoingLinks& ol, const double& r) { return OutgoingLinksRank(ol, r); });
+        auto contribs = outs_rank.template FlatMap<Contrib>(
+            [](const OutgoingLinksRank& p, auto emit) {
+                if (p.first.size() == 0) return;
+                double c = p.second / static_cast<double>(p.first.size());
+                for (const PageId& tgt : p.first) emit(Contrib(tgt, c));
+            });
+        auto dampen = [n_d](const Contrib& p) { return 0.85 * p.second + (1 - 0.85) / n_d; };
+        if (UseGpu)
+            ranks = thrill_gpu::ReduceToIndex(contribs, std::plus<double>(), num_pages).Map(dampen).Collapse();
+        else
+            ranks = contribs.ReduceToIndex(
+                [](const Contrib& p) { return static_cast<size_t>(p.first); },
+                [](const Contrib& a, const Contrib& b) { return Contrib(a.first, a.second + b.second); }, num_pages)
+                    .Map(dampen).Collapse();
+    }
+    return ranks.AllGather();
+}
 
 //! TeraSort's item (examples/terasort/terasort.cpp:31-42): 10 key bytes compared lexicographically, 90 payload bytes
 struct Record {
@@ -180,6 +222,23 @@ int main(int argc, char** argv) {
                 bool ok = cpu == gpu && cpu.size() == nr;
                 if (ctx.my_rank() == 0)
                     printf("%s TeraSort Records n=%zu cpu=%.3fs gpu=%.3fs\n", ok ? "PASS" : "FAIL", nr, t_cpu.SecondsDouble(), t_gpu.SecondsDouble());
+                if (!ok) g_failures++;
+            }
+            // ---- PageRank (cfg5's pipeline, examples/page_rank/page_rank.hpp:70-139), 10 iterations: ReduceToIndex on the GPU
+            //      against the stock operator; tolerance of the reference's own test (tests/examples/page_rank_test.cpp:94)
+            {
+                const size_t pages = 50000;
+                std::vector<double> cpu = PageRankRun<false>(ctx, pages, 10);
+                std::vector<double> gpu = PageRankRun<true>(ctx, pages, 10);
+                bool ok = cpu.size() == pages && gpu.size() == pages;
+                double maxdiff = 0, sum = 0;
+                for (size_t i = 0; ok && i < pages; ++i) {
+                    maxdiff = std::max(maxdiff, std::abs(cpu[i] - gpu[i]));
+                    sum += gpu[i];
+                }
+                ok = ok && maxdiff < 1e-6;
+                if (ctx.my_rank() == 0)
+                    printf("%s PageRank pages=%zu iterations=10 max|cpu-gpu|=%.3g sum=%.6f\n", ok ? "PASS" : "FAIL", pages, maxdiff, sum);
                 if (!ok) g_failures++;
             }
         });

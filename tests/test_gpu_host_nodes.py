@@ -17,7 +17,7 @@ def test_gpu_nodes_inside_thrill_single_worker():
     res = subprocess.run([BIN, "2000000"], env=env, capture_output=True, text=True, timeout=900)
     lines = [l for l in res.stdout.splitlines() if l.startswith(("PASS", "FAIL"))]
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
-    assert len(lines) == 9 and all(l.startswith("PASS") for l in lines), lines
+    assert len(lines) == 10 and all(l.startswith("PASS") for l in lines), lines
 
 
 @pytest.mark.skipif(not os.path.exists(BIN), reason="tests/host/_build/gpu_nodes_test not built")
@@ -29,4 +29,4 @@ def test_gpu_nodes_inside_thrill_two_workers_two_gpus():
     res = subprocess.run([BIN, "3000000"], env=env, capture_output=True, text=True, timeout=900)
     lines = [l for l in res.stdout.splitlines() if l.startswith(("PASS", "FAIL"))]
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
-    assert len(lines) == 9 and all(l.startswith("PASS") for l in lines), lines
+    assert len(lines) == 10 and all(l.startswith("PASS") for l in lines), lines
