@@ -75,7 +75,7 @@ int exchange_scatter(tg_ctx* ctx, const void* d_in, size_t n, const DigitFn& fn,
             u32* status;
             TG_TRY(tg_ws_get(ctx, WS_SORT_STATUS, (size_t)total * RADIX * 4, (void**)&status));
             TG_CUDA(ctx, cudaMemsetAsync(status, 0, (size_t)total * RADIX * 4, ctx->stream));
-            SegList sl = { d_tiles, chunkbase, total };
+            SegList sl = { d_tiles, chunkbase, total, nullptr };
             const int xprof = ctx->profile ? tg_prof_begin(ctx, TG_K_EXCHANGE) : -1;
             TG_TRY((launch_partition_peer<WORDS, DigitFn>(ctx, d_in, (u32)n, fn, status, sl, (Item* const*)d_dbase)));
             if (xprof >= 0) tg_prof_end(ctx, xprof);
@@ -96,7 +96,7 @@ int exchange_scatter(tg_ctx* ctx, const void* d_in, size_t n, const DigitFn& fn,
         u32* status;
         TG_TRY(tg_ws_get(ctx, WS_SORT_STATUS, (size_t)total * RADIX * 4, (void**)&status));
         TG_CUDA(ctx, cudaMemsetAsync(status, 0, (size_t)total * RADIX * 4, ctx->stream));
-        SegList sl = { d_tiles, chunkbase, total };
+        SegList sl = { d_tiles, chunkbase, total, nullptr };
         TG_TRY((launch_partition_seg<WORDS, DigitFn>(ctx, d_in, d_part, (u32)n, fn, status, sl)));
     }
     const int xprof = ctx->profile ? tg_prof_begin(ctx, TG_K_EXCHANGE) : -1;

@@ -212,8 +212,10 @@ __device__ __forceinline__ void rank_rows_unstable(const Item (&key)[ITEMS], u32
 struct SegList {
     const uint4* tiles;
     const u32* segbase;
-    u32 num_tiles;
+    u32 num_tiles;                  // number of tiles, or an upper bound of it if num_tiles_dev is set
+    const u32* num_tiles_dev;       // device-built lists (build_seg_tiles_device): the exact count lives on the device
 };
+__device__ __forceinline__ u32 seg_num_tiles(const SegList& sl) { return sl.num_tiles_dev ? __ldg(sl.num_tiles_dev) : sl.num_tiles; }
 
 // One tile: rank -> per-digit counts (published for the chained scan) -> scatter into the exchange buffer while
 // the look-back loads are in flight -> resolve the look-back -> coalesced write-out.
@@ -253,7 +255,7 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
     DigitFn fn = fn_param;
     fn.init();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u32 num_tiles = SEG ? sl.num_tiles : (n + TILE - 1) / TILE;
+    const u32 num_tiles = SEG ? seg_num_tiles(sl) : (n + TILE - 1) / TILE;
     const u32 lt = lanemask_lt();
     cnt_t* const whist_w = whist + warp * RADIX;
     const u32 whist_w_a = smem_u32(whist_w);
@@ -547,7 +549,7 @@ inline int sweep_debug() {
 template <int WORDS, int THREADS, int WPT, int MINB, class DigitFn, bool SEG = false, bool DBG = false, bool TMA = true, bool PEER = false,
           bool UNSTABLE = false>
 int launch_partition_v(tg_ctx* ctx, const void* in, void* out, u32 n, const DigitFn& fn, const u32* gbase, u32* status,
-                       const SegList& sl = SegList{ nullptr, nullptr, 0 }, typename ItemT<WORDS>::type* const* dbase = nullptr) {
+                       const SegList& sl = SegList{ nullptr, nullptr, 0, nullptr }, typename ItemT<WORDS>::type* const* dbase = nullptr) {
     typedef typename ItemT<WORDS>::type Item;
     constexpr int IPT = WPT / WORDS;
     typedef SweepCfg<WORDS, THREADS, IPT, TMA, DigitFn::kStoreDigit, PEER> C;

@@ -305,9 +305,11 @@ bool segmented_enabled() {
 // `npos` stable passes (digit positions pos[0..npos), least significant first) inside the segments given by the
 // histogram of the digit the items are currently partitioned by (seg_size on the host, seg_start on the device)
 // first_unstable: the first of these passes orders by a digit below which nothing has been ordered yet, and the items are
-// nothing but their key: it may run with the cheaper unstable ranking
+// nothing but their key: it may run with the cheaper unstable ranking.
+// seg_size == nullptr: the segment sizes are only known on the device (d_seg_size): the tile list is built there and nothing
+// waits for the host.
 template <int WORDS>
-int run_segmented_passes(tg_ctx* ctx, const PassList& pl, const int* pos, int npos, const u32* seg_size,
+int run_segmented_passes(tg_ctx* ctx, const PassList& pl, const int* pos, int npos, const u32* seg_size, const u32* d_seg_size,
                          const u32* d_seg_start, size_t n, void** src, void** dst, bool first_unstable = false) {
     typedef typename ItemT<WORDS>::type Item;
     if (npos == 0) return TG_OK;
@@ -316,7 +318,9 @@ int run_segmented_passes(tg_ctx* ctx, const PassList& pl, const int* pos, int np
     // has synchronised the stream since the previous use of buffer 1)
     uint4* d_tiles;
     u32 total = 0;
-    TG_TRY(build_tile_list(ctx, RADIX, seg_size, tile_items<WORDS>(), 1, WS_SEG_TILES, &d_tiles, &total));
+    const u32* d_total = nullptr;
+    if (seg_size) TG_TRY(build_tile_list(ctx, RADIX, seg_size, tile_items<WORDS>(), 1, WS_SEG_TILES, &d_tiles, &total));
+    else TG_TRY(build_seg_tiles_device(ctx, d_seg_size, d_seg_start, n, tile_items<WORDS>(), false, WS_SEG_TILES, &d_tiles, &d_total, &total));
     if (total == 0) return TG_OK;
     u32* tables;       // segcount [seg][npos][RADIX] | segbase [pos][seg][RADIX]
     const size_t table_words = (size_t)RADIX * npos * RADIX;
@@ -328,7 +332,7 @@ int run_segmented_passes(tg_ctx* ctx, const PassList& pl, const int* pos, int np
     TG_TRY(tg_ws_get(ctx, WS_SORT_STATUS2, (size_t)npos * pass_status_words * 4, (void**)&status));
     TG_CUDA(ctx, cudaMemsetAsync(segcount, 0, table_words * 4, ctx->stream));
     TG_CUDA(ctx, cudaMemsetAsync(status, 0, (size_t)npos * pass_status_words * 4, ctx->stream));
-    SegList sl = { d_tiles, nullptr, total };
+    SegList sl = { d_tiles, nullptr, total, d_total };
     DigitList<RadixDigit> dl;
     dl.n = npos;
     for (int i = 0; i < 4; ++i) {
@@ -362,7 +366,7 @@ int run_fixup(tg_ctx* ctx, const tg_key_desc* desc, bool plain_u64, const Prefix
         TG_LAUNCH_T(ctx, TG_K_FIXUP, (prefix_fixup_kernel<WORDS, true>), grid, FIX_THREADS, 0, (const Item*)src, (Item*)dst, (u32)n, kv, pm, d_fail);
     else
         TG_LAUNCH_T(ctx, TG_K_FIXUP, (prefix_fixup_kernel<WORDS, false>), grid, FIX_THREADS, 0, (const Item*)src, (Item*)dst, (u32)n, kv, pm, d_fail);
-    u32* h_fail = (u32*)ctx->pinned;
+    u32* h_fail = (u32*)ctx->pinned + 7168;       // (byte offset 28 KB of the pinned scratch: the callers keep the histogram / OR-AND words at its start)
     TG_CUDA(ctx, cudaMemcpyAsync(h_fail, d_fail, 4, cudaMemcpyDeviceToHost, ctx->stream));
     TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *ok = *h_fail == 0;
@@ -433,6 +437,50 @@ int prefix_sort_fast(tg_ctx* ctx, const tg_key_desc* desc, const PassList& pl, b
     u32* cstatus;
     TG_TRY(tg_ws_get(ctx, WS_SORT_STATUS, (size_t)ctotal * RADIX * 4, (void**)&cstatus));
     TG_CUDA(ctx, cudaMemsetAsync(cstatus, 0, (size_t)ctotal * RADIX * 4, ctx->stream));
+    // Items that are nothing but their key (equal keys are indistinguishable) need no stability from the pass on the most
+    // significant digit nor from the first pass below it: the cheaper unstable ranking (TG_UNSTABLE_RANK=0 switches it off)
+    static const bool unstable_ok = !(getenv("TG_UNSTABLE_RANK") && atoi(getenv("TG_UNSTABLE_RANK")) == 0);
+    const bool key_only = unstable_ok && desc->key_bytes == desc->item_bytes && desc->key_offset == 0;
+    static const bool optimistic = !(getenv("TG_SORT_OPTIMISTIC") && atoi(getenv("TG_SORT_OPTIMISTIC")) == 0);
+    if (bitwise && optimistic) {
+        // Integer keys: the digits are fixed by the assumed top bit, so everything can be queued without waiting for the histogram
+        // — the pass on the top digit, the tile list of its buckets (built on the device), the passes inside them, the finishing
+        // pass — and the host looks at the histogram, the OR/AND of the keys and the finishing pass's flag once, at the end.  A
+        // wrong assumption (bits above the top digit vary, the digit has few values, a group was too long) leaves a permutation of
+        // the input in *src for the general path, exactly as before.
+        int ppos[MAX_PASSES];
+        for (int i = 0; i < K - 1; ++i) ppos[i] = i;
+        const u64 kmask = kbits >= 64 ? ~0ull : (((1ull << kbits) - 1) << kb0);
+        PrefixMask pmo = { 0, (kmask >> kb0) & ~((1ull << (pp.shift[0] - kb0)) - 1) };
+        {
+            SegList sl = { d_ctiles, chunkbase, ctotal, nullptr };
+            if (key_only) TG_TRY((launch_partition_seg_unstable<WORDS, RadixDigit>(ctx, *src, *dst, (u32)n, top_fn, cstatus, sl)));
+            else TG_TRY((launch_partition_seg<WORDS, RadixDigit>(ctx, *src, *dst, (u32)n, top_fn, cstatus, sl)));
+            void* t = *src; *src = *dst; *dst = t;
+        }
+        TG_TRY((run_segmented_passes<WORDS>(ctx, pp, ppos, K - 1, nullptr, totals, gbase_top, n, src, dst, key_only)));
+        bool ok = false;
+        TG_TRY((run_fixup<WORDS>(ctx, desc, plain_u64, pmo, *src, *dst, n, fail, &ok)));          // (the one synchronisation)
+        int nonempty_o = 0;
+        for (int d = 0; d < RADIX; ++d) nonempty_o += h_totals[d] ? 1 : 0;
+        const int w = pp.word[0];
+        const u64 diff = (h_orand[2 * w] ^ h_orand[2 * w + 1]) & kmask;
+        const int tb_act = diff ? 64 - __builtin_clzll(diff) - kb0 : 0;          // most significant varying key bit + 1
+        if (tb_act != tb) ctx->spec_top_bit = tb_act > 8 ? tb_act : 8;           // what the next sort on this ctx should assume
+        if (tb_act > tb || nonempty_o < 32) {
+            if (tb_act <= tb && (tb_act + 7) / 8 < K + 2) ctx->prefix_spec_penalty = 8;
+            return TG_OK;                                                         // (*src: a permutation of the input)
+        }
+        if (ok) {
+            void* t = *src; *src = *dst; *dst = t;
+            *taken = true;
+        }
+        else {
+            ctx->prefix_sort_penalty = 8;
+            ctx->prefix_sort_fallbacks++;
+        }
+        return TG_OK;
+    }
     TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 
     int nonempty = 0;
@@ -467,19 +515,15 @@ int prefix_sort_fast(tg_ctx* ctx, const tg_key_desc* desc, const PassList& pl, b
         for (int i = 0; i < K - 1; ++i) prefix_pos[i] = active[nactive - K + i];
         pm = prefix_mask(desc, active[nactive - K]);
     }
-    // Items that are nothing but their key (equal keys are indistinguishable) need no stability from the pass on the most
-    // significant digit nor from the first pass below it: the cheaper unstable ranking (TG_UNSTABLE_RANK=0 switches it off)
-    static const bool unstable_ok = !(getenv("TG_UNSTABLE_RANK") && atoi(getenv("TG_UNSTABLE_RANK")) == 0);
-    const bool key_only = unstable_ok && desc->key_bytes == desc->item_bytes && desc->key_offset == 0;
     // (1) most significant digit: segmented pass over the chunks
     {
-        SegList sl = { d_ctiles, chunkbase, ctotal };
+        SegList sl = { d_ctiles, chunkbase, ctotal, nullptr };
         if (key_only) TG_TRY((launch_partition_seg_unstable<WORDS, RadixDigit>(ctx, *src, *dst, (u32)n, top_fn, cstatus, sl)));
         else TG_TRY((launch_partition_seg<WORDS, RadixDigit>(ctx, *src, *dst, (u32)n, top_fn, cstatus, sl)));
         void* t = *src; *src = *dst; *dst = t;
     }
     // (2) the other K-1 prefix digits inside the buckets of (1)
-    TG_TRY((run_segmented_passes<WORDS>(ctx, pp, prefix_pos, K - 1, h_totals, gbase_top, n, src, dst, key_only)));
+    TG_TRY((run_segmented_passes<WORDS>(ctx, pp, prefix_pos, K - 1, h_totals, nullptr, gbase_top, n, src, dst, key_only)));
     // (3) finishing pass
     bool ok = false;
     TG_TRY((run_fixup<WORDS>(ctx, desc, plain_u64, pm, *src, *dst, n, fail, &ok)));
@@ -561,7 +605,7 @@ int radix_sort_impl(tg_ctx* ctx, const tg_key_desc* desc, const PassList& pl, vo
         if (segmented_enabled() && K >= 2 && nonempty >= 32) {
             // most significant digit first (global pass), then the other K-1 digits inside its buckets
             TG_TRY(run_pass(top));
-            TG_TRY((run_segmented_passes<WORDS>(ctx, pl, active + (nactive - K), K - 1, h_hist + top * RADIX,
+            TG_TRY((run_segmented_passes<WORDS>(ctx, pl, active + (nactive - K), K - 1, h_hist + top * RADIX, nullptr,
                                                  gbase + (size_t)top * RADIX, n, &src, &dst)));
         }
         else

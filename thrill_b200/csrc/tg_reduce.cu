@@ -721,7 +721,7 @@ int run_partitioned_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 n, void
         u32* cstatus;
         TG_TRY(tg_ws_get(ctx, WS_SORT_STATUS, (size_t)ctotal * RADIX * 4, (void**)&cstatus));
         TG_CUDA(ctx, cudaMemsetAsync(cstatus, 0, (size_t)ctotal * RADIX * 4, ctx->stream));
-        SegList csl = { d_ctiles, chunkbase, ctotal };
+        SegList csl = { d_ctiles, chunkbase, ctotal, nullptr };
         TG_TRY((launch_partition_seg<2, HotLevelDigit>(ctx, d_in, bufA, (u32)n, fn1, cstatus, csl)));
     }
     u32* h_tot1 = (u32*)ctx->pinned;
@@ -743,7 +743,7 @@ int run_partitioned_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 n, void
     TG_TRY(tg_ws_get(ctx, WS_SORT_STATUS2, (size_t)total * RADIX * 4, (void**)&status));
     TG_CUDA(ctx, cudaMemsetAsync(segcount, 0, table_words * 4, ctx->stream));
     TG_CUDA(ctx, cudaMemsetAsync(status, 0, (size_t)total * RADIX * 4, ctx->stream));
-    SegList sl = { d_tiles, segbase, total };
+    SegList sl = { d_tiles, segbase, total, nullptr };
     DigitList<HashLevelDigit> dl;
     dl.n = 1;
     for (int i = 0; i < 4; ++i) dl.fn[i] = HashLevelDigit{ AGG_SHIFT2 };

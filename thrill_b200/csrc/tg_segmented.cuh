@@ -131,7 +131,8 @@ __global__ void __launch_bounds__(512) seg_count_kernel(const typename ItemT<WOR
     for (int p = 0; p < NPOS; ++p) dl.fn[p].init();
     __shared__ u32 sh[NPOS * RADIX];
     constexpr int U = 4;
-    for (u32 j = blockIdx.x; j < sl.num_tiles; j += gridDim.x) {
+    const u32 num_tiles = seg_num_tiles(sl);
+    for (u32 j = blockIdx.x; j < num_tiles; j += gridDim.x) {
         const uint4 t = __ldg(&sl.tiles[j]);
         for (int i = threadIdx.x; i < NPOS * RADIX; i += blockDim.x) sh[i] = 0;
         __syncthreads();
@@ -232,6 +233,84 @@ inline int build_tile_list(tg_ctx* ctx, int nseg, const u32* seg_size, u32 tile,
     return TG_OK;
 }
 
+// ---- the same interleaved tile list for the RADIX buckets of a pass, built on the device (no host round trip) ----------------
+// aux (RADIX * 4 + 8 words): row0[s] (first status row of segment s) | sortrank[s] (position of s when the segments are ordered
+// by tile count, descending) | snt[k] (tile counts in that order) | P[k] (prefix sums of snt, RADIX + 1 entries) | total.
+// Round r of the list holds the r-th tile of every segment that has one, in sorted order: the position of tile (s, r) is
+// A(r) + sortrank[s] with A(r) = sum over segments of min(tiles, r) = r * C(r) + (total - P[C(r)]), C(r) = #segments with > r tiles.
+static __global__ void __launch_bounds__(RADIX) seg_tiles_prepare_kernel(const u32* __restrict__ seg_size, u32 tile, int drop_last,
+                                                                         u32* __restrict__ aux, u32* __restrict__ total_out) {
+    __shared__ u32 nt[RADIX], incl[RADIX], snt[RADIX];
+    const int s = threadIdx.x;
+    const u32 size = (drop_last && s == RADIX - 1) ? 0u : seg_size[s];
+    nt[s] = (size + tile - 1) / tile;
+    incl[s] = nt[s];
+    __syncthreads();
+    for (int o = 1; o < RADIX; o <<= 1) {
+        const u32 v = s >= o ? incl[s - o] : 0u;
+        __syncthreads();
+        incl[s] += v;
+        __syncthreads();
+    }
+    u32 rank = 0;
+    for (int q = 0; q < RADIX; ++q) rank += (nt[q] > nt[s] || (nt[q] == nt[s] && q < s)) ? 1u : 0u;
+    snt[rank] = nt[s];
+    aux[s] = incl[s] - nt[s];                  // row0
+    aux[RADIX + s] = rank;                     // sortrank
+    __syncthreads();
+    aux[2 * RADIX + s] = snt[s];
+    u32 p = snt[s];
+    incl[s] = p;
+    __syncthreads();
+    for (int o = 1; o < RADIX; o <<= 1) {
+        const u32 v = s >= o ? incl[s - o] : 0u;
+        __syncthreads();
+        incl[s] += v;
+        __syncthreads();
+    }
+    aux[3 * RADIX + s + 1] = incl[s];          // P[s + 1]
+    if (s == 0) aux[3 * RADIX] = 0;
+    if (s == RADIX - 1) { aux[4 * RADIX + 1] = incl[s]; *total_out = incl[s]; }
+}
+
+static __global__ void __launch_bounds__(256) seg_tiles_fill_kernel(const u32* __restrict__ seg_size, const u32* __restrict__ seg_start, u32 tile,
+                                                                    int drop_last, const u32* __restrict__ aux, uint4* __restrict__ tiles) {
+    __shared__ u32 row0[RADIX], snt[RADIX], P[RADIX + 1], srank[RADIX];
+    for (int i = threadIdx.x; i < RADIX; i += blockDim.x) { row0[i] = aux[i]; srank[i] = aux[RADIX + i]; snt[i] = aux[2 * RADIX + i]; P[i] = aux[3 * RADIX + i]; }
+    if (threadIdx.x == 0) P[RADIX] = aux[4 * RADIX];
+    __syncthreads();
+    const u32 total = P[RADIX];
+    const u32 row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= total) return;
+    int lo = 0, hi = RADIX;                    // last segment with row0 <= row that has tiles
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (row0[mid] <= row) lo = mid; else hi = mid; }
+    const u32 sg = (u32)lo, r = row - row0[sg];
+    int c0 = 0, c1 = RADIX;                    // C(r) = number of entries of the descending snt that are > r
+    while (c0 < c1) { const int mid = (c0 + c1) >> 1; if (snt[mid] > r) c0 = mid + 1; else c1 = mid; }
+    const u32 C = (u32)c0;
+    const u32 pos = r * C + (total - P[C]) + srank[sg];
+    const u32 size = (drop_last && sg == RADIX - 1) ? 0u : seg_size[sg];
+    const u32 off = r * tile;
+    tiles[pos] = make_uint4(seg_start[sg] + off, size - off < tile ? size - off : tile, row, (sg << 20) | r);
+}
+
+// tile list of the RADIX segments whose sizes / starts are DEVICE arrays; *d_tiles (workspace `ws_slot`) holds at most
+// bound = ceil(n / tile) + RADIX tiles, the exact count is at *d_total (inside the same workspace)
+inline int build_seg_tiles_device(tg_ctx* ctx, const u32* d_seg_size, const u32* d_seg_start, size_t n, u32 tile, bool drop_last,
+                                  int ws_slot, uint4** d_tiles, const u32** d_total, u32* bound_out) {
+    const u32 bound = (u32)((n + tile - 1) / tile) + RADIX;
+    unsigned char* base;
+    TG_TRY(tg_ws_get(ctx, ws_slot, (size_t)bound * sizeof(uint4) + (4 * RADIX + 8) * 4 + 64, (void**)&base));
+    *d_tiles = (uint4*)base;
+    u32* aux = (u32*)(base + (size_t)bound * sizeof(uint4));
+    u32* total = aux + 4 * RADIX + 4;
+    TG_LAUNCH(ctx, seg_tiles_prepare_kernel, 1, RADIX, 0, d_seg_size, tile, drop_last ? 1 : 0, aux, total);
+    TG_LAUNCH(ctx, seg_tiles_fill_kernel, (bound + 255) / 256, 256, 0, d_seg_size, d_seg_start, tile, drop_last ? 1 : 0, (const u32*)aux, *d_tiles);
+    *d_total = total;
+    *bound_out = bound;
+    return TG_OK;
+}
+
 // chunk geometry of a chunked pass over n items: ~2 chunks per SM, whole tiles
 struct ChunkGeom {
     u32 chunk_items;
@@ -284,7 +363,7 @@ int partition_chunked(tg_ctx* ctx, const void* in, void* out, size_t n, const Di
     u32* status;
     TG_TRY(tg_ws_get(ctx, WS_SORT_STATUS, (size_t)total * RADIX * 4, (void**)&status));
     TG_CUDA(ctx, cudaMemsetAsync(status, 0, (size_t)total * RADIX * 4, ctx->stream));
-    SegList sl = { d_tiles, chunkbase, total };
+    SegList sl = { d_tiles, chunkbase, total, nullptr };
     return launch_partition_seg<WORDS, DigitFn>(ctx, in, out, (u32)n, fn, status, sl);
 }
 
