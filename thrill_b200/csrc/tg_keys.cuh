@@ -29,6 +29,12 @@ __host__ __device__ inline bool canonidx_less(const CanonIdx& a, const CanonIdx&
     return a.idx < b.idx;
 }
 
+// most significant byte of a canonical key (the order of the top bytes is the order of the keys' first byte-ranges)
+__host__ __device__ inline u32 canon_top_byte(const Canon& c, const KeyView& kv) {
+    if (kv.kind == TG_KEY_UINT_LE) return (u32)(c.lo >> (8 * (kv.bytes > 8 ? 8 : kv.bytes) - 8)) & 0xffu;
+    return (u32)(c.hi >> 56);
+}
+
 // byte j of an item held as little-endian u64 words
 template <class Item>
 __device__ __forceinline__ u32 item_byte(const Item& v, u32 j) {

@@ -50,6 +50,7 @@ struct RadixDigit {
     u32 flip;
     static constexpr bool kStoreDigit = false;      // cheap to recompute in the write-out
     static constexpr bool kHasDrop = false;         // true: digit RADIX-1 means "leave this item out of the output"
+    static constexpr int kScratch = 0;              // bytes of CTA shared memory the functor wants (filled by init_shared)
     __device__ __forceinline__ void init() {}
     template <class Item>
     __device__ __forceinline__ u32 operator()(const Item& v, u32) const {
@@ -103,7 +104,7 @@ __device__ __forceinline__ u32 match_digit8(u32 d) {
 
 // tile geometry of one launch configuration: THREADS threads, each owning IPT items of WORDS 8-byte words
 constexpr int PEER_MAX = 32;        // destinations of a partition pass that stores into peer windows (<= TG_MAX_RANKS used)
-template <int WORDS, int THREADS, int IPT, bool TMA = true, bool STORE = true, bool PEER = false>
+template <int WORDS, int THREADS, int IPT, bool TMA = true, bool STORE = true, bool PEER = false, int SCRATCH = 0>
 struct SweepCfg {
     static constexpr int ITEM_BYTES = 8 * WORDS;
     static constexpr int ITEMS = IPT;
@@ -115,7 +116,7 @@ struct SweepCfg {
     static constexpr int NBUF = TMA ? 2 : 1;                // landing + exchange, or the exchange buffer alone
     // buffers | warp counters [NWARPS][RADIX] | goff [RADIX] | warp_tot [16] | mbar [2] | digit bytes [TILE] (only if the digit
     // function's result is kept, kStoreDigit) | slack
-    static constexpr int SMEM = NBUF * BUF_BYTES + NWARPS * RADIX * (int)sizeof(unsigned short) + RADIX * 4 + 64 + 16 + (STORE ? TILE : 0) + (PEER ? PEER_MAX * 8 : 0) + 128;
+    static constexpr int SMEM = NBUF * BUF_BYTES + NWARPS * RADIX * (int)sizeof(unsigned short) + RADIX * 4 + 64 + 16 + (STORE ? TILE : 0) + (PEER ? PEER_MAX * 8 : 0) + SCRATCH + 128;
 };
 
 // exclusive scan of npass digit histograms -> global bases; skip[p] = 1 if one bin holds everything
@@ -233,7 +234,7 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
     typedef typename ItemT<WORDS>::type Item;
     // TMA = false: no landing buffer and no bulk copies; the items are loaded straight into registers (coalesced 8/16-byte
     // loads) and several small CTAs per SM hide each other's load latency and barriers instead of the double buffer
-    typedef SweepCfg<WORDS, THREADS, IPT, TMA, DigitFn::kStoreDigit, PEER> C;
+    typedef SweepCfg<WORDS, THREADS, IPT, TMA, DigitFn::kStoreDigit, PEER, DigitFn::kScratch> C;
     constexpr int ITEMS = C::ITEMS, TILE = C::TILE, NWARPS = C::NWARPS;
     // look-back batch (predecessors fetched concurrently): inside a segment the predecessor finished a wave ago, one or two
     // loads find its inclusive prefix; the plain chained scan over concurrently processed tiles needs a deep batch
@@ -251,9 +252,11 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
     u64* const mbar = reinterpret_cast<u64*>(warp_tot + 16);                     // [2]
     unsigned char* const dig = reinterpret_cast<unsigned char*>(mbar + 2);       // [TILE], only if kStoreDigit
     Item** const dptr = reinterpret_cast<Item**>(dig + (DigitFn::kStoreDigit ? TILE : 0));      // [PEER_MAX], only if PEER
+    unsigned char* const fscratch = reinterpret_cast<unsigned char*>(dptr + (PEER ? PEER_MAX : 0));  // [kScratch], the functor's
 
     DigitFn fn = fn_param;
     fn.init();
+    if constexpr (DigitFn::kScratch > 0) fn.init_shared(fscratch, (int)threadIdx.x, THREADS);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 num_tiles = SEG ? seg_num_tiles(sl) : (n + TILE - 1) / TILE;
     const u32 lt = lanemask_lt();
@@ -552,7 +555,7 @@ int launch_partition_v(tg_ctx* ctx, const void* in, void* out, u32 n, const Digi
                        const SegList& sl = SegList{ nullptr, nullptr, 0, nullptr }, typename ItemT<WORDS>::type* const* dbase = nullptr) {
     typedef typename ItemT<WORDS>::type Item;
     constexpr int IPT = WPT / WORDS;
-    typedef SweepCfg<WORDS, THREADS, IPT, TMA, DigitFn::kStoreDigit, PEER> C;
+    typedef SweepCfg<WORDS, THREADS, IPT, TMA, DigitFn::kStoreDigit, PEER, DigitFn::kScratch> C;
     auto kern = partition_kernel<WORDS, THREADS, IPT, MINB, DigitFn, SEG, DBG, TMA, PEER, UNSTABLE>;
     int ctas_per_sm = 0;
     auto it = ctx->kernel_cfg.find((const void*)kern);

@@ -161,6 +161,7 @@ struct HashDigit {
     u32 p;
     static constexpr bool kStoreDigit = true;
     static constexpr bool kHasDrop = false;
+    static constexpr int kScratch = 0;
     __device__ __forceinline__ void init() {}
     __device__ __forceinline__ u32 operator()(const ulonglong2& v, u32) const { return (u32)(key_hash(v.x) % p); }
 };
@@ -234,6 +235,7 @@ struct HashLevelDigit {
     int shift;
     static constexpr bool kStoreDigit = true;
     static constexpr bool kHasDrop = false;
+    static constexpr int kScratch = 0;
     __device__ __forceinline__ void init() {}
     __device__ __forceinline__ u32 operator()(const ulonglong2& v, u32) const { return (u32)(key_hash(v.x) >> shift) & (RADIX - 1); }
 };
@@ -563,6 +565,7 @@ struct HotLevelDigit {
     u32 nhot;
     static constexpr bool kStoreDigit = true;
     static constexpr bool kHasDrop = true;
+    static constexpr int kScratch = 0;
     __device__ __forceinline__ void init() { nhot = ht->nhot; }
     __device__ __forceinline__ u32 level(u64 h) const { return (((u32)(h >> shift) & (RADIX - 1)) * (RADIX - 1)) >> RADIX_BITS; }
     __device__ __forceinline__ u32 operator()(const ulonglong2&, u32 pos) const { return __ldg(&dig[pos]); }
@@ -815,6 +818,7 @@ struct RangeDigit {
     u32 p;
     static constexpr bool kStoreDigit = true;
     static constexpr bool kHasDrop = false;
+    static constexpr int kScratch = 0;
     __device__ __forceinline__ void init() {}
     __device__ __forceinline__ u32 operator()(const ulonglong2& v, u32) const {
         return v.x < size ? (u32)(v.x * p / size) : p - 1;

@@ -38,36 +38,61 @@ struct SplitterDigit {
     u64 gbase;
     KeyView kv;
     const u64* gbase_dev;          // if set: the worker's global index base, written by select_splitters_kernel
+    const unsigned char* lut;      // if set: [256] lower | [256] upper bucket bounds by the most significant key byte (splitter_lut_kernel)
+    const CanonIdx* s_spl;         // shared-memory copies (init_shared)
+    const unsigned char* s_lut;
     static constexpr bool kStoreDigit = true;
     static constexpr bool kHasDrop = false;
-    __device__ __forceinline__ void init() { if (gbase_dev) gbase = *gbase_dev; }
+    static constexpr int kScratch = TG_MAX_RANKS * 24 + 512;
+    __device__ __forceinline__ void init() { if (gbase_dev) gbase = *gbase_dev; s_spl = spl; s_lut = nullptr; }
+    // the splitters and the lookup table into the CTA's shared memory (called by every thread before the kernel's first barrier)
+    __device__ __forceinline__ void init_shared(unsigned char* scratch, int tid, int nthreads) {
+        if (!lut) return;
+        u64* w = reinterpret_cast<u64*>(scratch);
+        const u64* g = reinterpret_cast<const u64*>(spl);
+        for (int i = tid; i < (int)nspl * 3; i += nthreads) w[i] = g[i];
+        unsigned char* l = scratch + TG_MAX_RANKS * 24;
+        for (int i = tid; i < 512; i += nthreads) l[i] = lut[i];
+        s_spl = reinterpret_cast<const CanonIdx*>(scratch);
+        s_lut = l;
+    }
     template <class Item>
     __device__ __forceinline__ u32 operator()(const Item& v, u32 pos) const {
-        if (kv.kind == TG_KEY_UINT_LE && kv.bytes == 8 && (kv.off & 7) == 0) {
-            // integer key in one item word: search on the key alone (8-byte loads), then step over the splitters that tie with it
-            // and precede the item by global index (EqualSampleGreaterIndex, api/sort.hpp:424-426)
-            u64 k = item_word(v, (int)(kv.off >> 3));
-            if (kv.desc) k = ~k;
-            u32 lo = 0, hi = nspl;
-            while (lo < hi) {
-                const u32 mid = (lo + hi) >> 1;
-                if (spl[mid].lo < k) lo = mid + 1; else hi = mid;
-            }
-            const u64 gi = gbase + pos;
-            while (lo < nspl && spl[lo].lo == k && spl[lo].idx < gi) ++lo;
-            return lo;
-        }
-        Canon k = canon_key(v, kv);
-        CanonIdx me = { k.hi, k.lo, gbase + pos };
+        const bool int_key = kv.kind == TG_KEY_UINT_LE && kv.bytes == 8 && (kv.off & 7) == 0;
+        Canon k;
+        if (int_key) { k.hi = 0; k.lo = item_word(v, (int)(kv.off >> 3)); if (kv.desc) k.lo = ~k.lo; }
+        else k = canon_key(v, kv);
         u32 lo = 0, hi = nspl;
+        if (s_lut) {
+            // most keys fall into a byte range that holds no splitter: one shared-memory byte decides
+            const u32 tb = canon_top_byte(k, kv);
+            lo = s_lut[tb]; hi = s_lut[256 + tb];
+            if (lo == hi) return lo;
+        }
+        const CanonIdx me = { k.hi, k.lo, gbase + pos };
         while (lo < hi) {
-            u32 mid = (lo + hi) >> 1;
-            CanonIdx s = spl[mid];
+            const u32 mid = (lo + hi) >> 1;
+            const CanonIdx s = s_spl[mid];
             if (canonidx_less(s, me)) lo = mid + 1; else hi = mid;
         }
         return lo;
     }
 };
+
+// lut[b] = number of splitters whose most significant key byte is < b, lut[256 + b] = ... <= b: a key with top byte b belongs to
+// a bucket in [lut[b], lut[256 + b]]
+__global__ void splitter_lut_kernel(const CanonIdx* __restrict__ spl, u32 nspl, KeyView kv, unsigned char* __restrict__ lut) {
+    const u32 b = threadIdx.x;
+    u32 lt = 0, le = 0;
+    for (u32 j = 0; j < nspl; ++j) {
+        const Canon c = { spl[j].hi, spl[j].lo };
+        const u32 t = canon_top_byte(c, kv);
+        lt += t < b ? 1u : 0u;
+        le += t <= b ? 1u : 0u;
+    }
+    lut[b] = (unsigned char)lt;
+    lut[256 + b] = (unsigned char)le;
+}
 
 // ---- sampling: gather items at pseudo-random positions (OnPreOpFile, api/sort.hpp:162-170) --------------
 template <int WORDS>
@@ -347,11 +372,11 @@ bool classify_first() {
 // canonical key is described by kv.  Collective (one ncclAllGather).
 template <int WORDS>
 int device_splitters(tg_ctx* ctx, const KeyView& kv, const void* d_items, size_t n_local, uint64_t rng_seed, bool too_large,
-                     CanonIdx** d_spl_out, u64** d_ctl_out) {
+                     CanonIdx** d_spl_out, u64** d_ctl_out, unsigned char** d_lut_out = nullptr) {
     typedef typename ItemT<WORDS>::type Item;
     const int p = ctx->nranks, me = ctx->rank;
     unsigned char* d_samp;      // [p] gathered slots | my slot | splitters | ctl
-    TG_TRY(tg_ws_get(ctx, WS_SAMPLES, (size_t)(p + 1) * SAMPLE_SLOT_BYTES + 4096, (void**)&d_samp));
+    TG_TRY(tg_ws_get(ctx, WS_SAMPLES, (size_t)(p + 1) * SAMPLE_SLOT_BYTES + 8192, (void**)&d_samp));
     unsigned char* d_mine = d_samp + (size_t)p * SAMPLE_SLOT_BYTES;
     CanonIdx* d_spl = reinterpret_cast<CanonIdx*>(d_mine + SAMPLE_SLOT_BYTES);
     u64* d_ctl = reinterpret_cast<u64*>(d_spl + TG_MAX_RANKS);
@@ -376,6 +401,9 @@ int device_splitters(tg_ctx* ctx, const KeyView& kv, const void* d_items, size_t
     }
     TG_NCCL(ctx, ncclAllGather(d_mine, d_samp, SAMPLE_SLOT_BYTES, ncclUint8, ctx->comm, ctx->stream));
     TG_LAUNCH(ctx, select_splitters_kernel, (p * SAMPLE_MAX + 255) / 256, 256, 0, (const unsigned char*)d_samp, p, me, d_spl, d_ctl);
+    unsigned char* d_lut = reinterpret_cast<unsigned char*>(d_ctl + 8);
+    TG_LAUNCH(ctx, splitter_lut_kernel, 1, 256, 0, (const CanonIdx*)d_spl, (u32)(p - 1), kv, d_lut);
+    if (d_lut_out) *d_lut_out = d_lut;
     *d_spl_out = d_spl;
     *d_ctl_out = d_ctl;
     return TG_OK;
@@ -407,7 +435,8 @@ int sort_multi_impl(tg_ctx* ctx, const tg_key_desc* desc, const KeyView& kv, voi
     // one all-gather, splitters selected on the device by every rank
     CanonIdx* d_spl;
     u64* d_ctl;
-    TG_TRY((device_splitters<WORDS>(ctx, kv, d_in, n_local, rng_seed, too_large, &d_spl, &d_ctl)));
+    unsigned char* d_lut;
+    TG_TRY((device_splitters<WORDS>(ctx, kv, d_in, n_local, rng_seed, too_large, &d_spl, &d_ctl, &d_lut)));
     const u32 nspl = (u32)(p - 1);
     u64* h_ctl = h + 3072;                           // byte offset 24 KB: ctl[4] | splitters
     CanonIdx* h_spl = (CanonIdx*)(h_ctl + 4);
@@ -417,7 +446,7 @@ int sort_multi_impl(tg_ctx* ctx, const tg_key_desc* desc, const KeyView& kv, voi
     if (classify_first()) {
         // The reference's own order (api/sort.hpp:615-742): classify + scatter by the splitters (TransmitItems) and the exchange
         // — here one kernel that stores every item into its destination worker's window — then sort what was received.
-        SplitterDigit fn = { d_spl, nspl, 0, kv, d_ctl };
+        SplitterDigit fn = { d_spl, nspl, 0, kv, d_ctl, d_lut, nullptr, nullptr };
         XchgResult xr;
         TG_TRY((exchange_scatter<WORDS, SplitterDigit>(ctx, d_in, too_large ? 0 : n_local, fn, &xr)));      // (synchronises once)
         if (h_ctl[3]) return tg_set_error(ctx, TG_ERR_TOO_LARGE, "sort: a worker holds 2^30 or more items");
@@ -625,10 +654,11 @@ int sort_records_impl(tg_ctx* ctx, const tg_key_desc* desc, void* d_in, size_t n
     if (n) TG_LAUNCH(ctx, make_tuples_kernel, ctx->sm_count * 8, 256, 0, (const u32*)d_in, (u32)n, rb / 4, desc->key_offset, desc->key_bytes, d_tup);
     CanonIdx* d_spl;
     u64* d_ctl;
-    TG_TRY((device_splitters<2>(ctx, tkv, d_tup, n_local, rng_seed, too_large, &d_spl, &d_ctl)));
+    unsigned char* d_lut;
+    TG_TRY((device_splitters<2>(ctx, tkv, d_tup, n_local, rng_seed, too_large, &d_spl, &d_ctl, &d_lut)));
     u64* h_ctl = (u64*)ctx->pinned + 3072;
     TG_CUDA(ctx, cudaMemcpyAsync(h_ctl, d_ctl, 32, cudaMemcpyDeviceToHost, ctx->stream));
-    SplitterDigit fn = { d_spl, (u32)(p - 1), 0, tkv, d_ctl };
+    SplitterDigit fn = { d_spl, (u32)(p - 1), 0, tkv, d_ctl, d_lut, nullptr, nullptr };
     TG_TRY(xwin_negotiate(ctx));
     // destination histogram and the stable partition of the TUPLES by destination (local), then the records follow them
     u32 *d_tot = nullptr, *d_gb = nullptr;
@@ -757,7 +787,7 @@ int tg_classify_scatter(tg_ctx* ctx, const tg_key_desc* desc, const void* d_in, 
     CanonIdx* d_spl;
     TG_TRY(tg_ws_get(ctx, WS_SAMPLES, (size_t)p * sizeof(CanonIdx) + 256, (void**)&d_spl));
     if (p > 1) TG_CUDA(ctx, cudaMemcpyAsync(d_spl, spl.data(), (p - 1) * sizeof(CanonIdx), cudaMemcpyHostToDevice, ctx->stream));
-    SplitterDigit fn = { d_spl, p - 1, global_index_base, kv, nullptr };
+    SplitterDigit fn = { d_spl, p - 1, global_index_base, kv, nullptr, nullptr, nullptr, nullptr };
     u32* d_counts = nullptr;
     if (desc->item_bytes == 8) TG_TRY((partition_chunked<1, SplitterDigit>(ctx, d_in, d_out, n, fn, &d_counts, nullptr)));
     else TG_TRY((partition_chunked<2, SplitterDigit>(ctx, d_in, d_out, n, fn, &d_counts, nullptr)));

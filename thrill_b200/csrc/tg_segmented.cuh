@@ -36,6 +36,8 @@ __global__ void __launch_bounds__(512) chunk_hist_kernel(const typename ItemT<WO
     fn.init();
     constexpr int U = 32 / (4 * WORDS);      // 64 bytes of loads in flight per thread
     __shared__ u32 sh[RADIX];
+    __shared__ __align__(16) unsigned char fscratch[DigitFn::kScratch > 0 ? DigitFn::kScratch : 16];
+    if constexpr (DigitFn::kScratch > 0) fn.init_shared(fscratch, (int)threadIdx.x, (int)blockDim.x);
     for (int i = threadIdx.x; i < RADIX; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     const u32 lo = blockIdx.x * chunk_items;
