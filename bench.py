@@ -457,6 +457,25 @@ def bench_terasort(args, ctx, world, rank, hbm_peak, steps=2, warmup=1):
             "step_share": {"gather_ms": gather_ms / steps, "tuple_partition_ms": part_ms / steps, "exchange_ms": xchg_ms / steps, "step_ms": step}}
 
 
+def e2e_in_thrill(n=20000000):
+    """The drop-in inside a real Thrill job (tests/host/gpu_nodes_test: api::Run, 1 worker, the unmodified reference library
+    around the GPU nodes): wall time of Generate -> thrill_gpu::Sort -> AllGather against the stock Sort on the same worker
+    thread.  BlockPool memory is pageable here: this is the number a Thrill user gets without pinning it."""
+    exe = os.path.join(ROOT, "tests", "host", "_build", "gpu_nodes_test")
+    if not os.path.exists(exe):
+        return None
+    env = dict(os.environ, THRILL_NET="mock", THRILL_LOCAL="1", THRILL_WORKERS_PER_HOST="1", THRILL_LOG="")
+    try:
+        res = subprocess.run([exe, str(n)], env=env, capture_output=True, text=True, timeout=600)
+    except Exception as e:          # noqa: BLE001
+        return {"error": str(e)[:200]}
+    out = {"binary": "tests/host/_build/gpu_nodes_test %d (THRILL_WORKERS_PER_HOST=1)" % n, "rc": res.returncode, "sections": []}
+    for l in res.stdout.splitlines():
+        if l.startswith(("PASS", "FAIL")):
+            out["sections"].append(l[:160])
+    return out
+
+
 def reduce_parity(ctx, world, rank, d_cdf):
     """exact-mode sample (integer-valued doubles: sums are order independent) through the same operator, every key on the
     worker the reference's ReduceByHash puts it on, sums equal to a numpy group-by of the same records"""
@@ -663,6 +682,8 @@ def main():
             except BaseException as e:          # noqa: BLE001
                 extra["reduce"]["cpu_baseline"] = {"error": str(e)[:200]}
 
+    if rank == 0 and world == 1 and args.metric == "sort" and not args.no_extras and not args.no_cpu_baseline:
+        extra["e2e_in_thrill"] = e2e_in_thrill()
     if rank == 0:
         cfg = workload_config(args.metric, n_item, world)
         line = {"metric": name, "value": main_res["value"], "unit": unit, "n_gpus": world, "steps": main_res["steps"],

@@ -588,27 +588,44 @@ __global__ void __launch_bounds__(256) gather_records_kernel(const u32* __restri
     }
 }
 
-// the exchange of the records: tuple g of the destination-partitioned tuple array names the record that becomes record
-// (g - first[d]) of this worker's share in destination d's window (dst[d], mapped peer memory or the local send buffer)
-struct RecDest {
-    u32* dst[TG_MAX_RANKS];
-    u32 first[TG_MAX_RANKS + 1];
-    int p;
-};
+// The exchange of the records, one launch per destination worker: tuple first + j of the destination-partitioned tuple array
+// names the record that becomes record j of this worker's share in the destination's window (mapped peer memory, or the local
+// send buffer).  The share is a contiguous stream of cnt * rec_words 32-bit words starting at a 4-byte-aligned address:
+// a thread assembles one 16-byte-aligned group of four stream words (they may come from two records) and issues ONE 128-bit
+// store — NVLink moves 16-byte stores at about twice the rate of 4-byte ones; only the first and last group of a stream are
+// written word by word.
 __global__ void __launch_bounds__(256) scatter_records_kernel(const u32* __restrict__ rec, const ulonglong2* __restrict__ ptuples,
-                                                               u32 n, u32 rec_words, u32 inv, const RecDest rd) {
-    for (u32 r0 = blockIdx.x * REC_BATCH; r0 < n; r0 += gridDim.x * REC_BATCH) {
-        const u32 nrec = n - r0 < REC_BATCH ? n - r0 : REC_BATCH, words = nrec * rec_words;
-#pragma unroll 4
-        for (u32 lt = threadIdx.x; lt < words; lt += 256) {
-            const u32 j = __umulhi(lt, inv), w = lt - j * rec_words, g = r0 + j;
-            int d = 0;
+                                                               u32 cnt, u32 rec_words, u32 inv, u32* __restrict__ dst) {
+    const u32 a = (u32)(((uintptr_t)dst >> 2) & 3u);             // stream word 0 sits at word `a` of its 16-byte group
+    uint4* const dst4 = reinterpret_cast<uint4*>(dst - a);
+    const u64 nwords = (u64)cnt * rec_words;
+    const u64 ngroups = (nwords + a + 3) / 4;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x; c < ngroups; c += stride) {
+        u32 val[4];
+        bool ok[4];
+        // (record, word) of the group's first stream word by one division, of the following ones by stepping
+        const u64 wfirst = 4 * c >= a ? 4 * c - a : 0;
+        u32 j = (u32)(wfirst / rec_words), ww = (u32)(wfirst - (u64)j * rec_words);
+        u32 src = j < cnt ? (u32)(__ldg(&ptuples[j].y) >> 32) : 0u;
 #pragma unroll
-            for (int q = 1; q < TG_MAX_RANKS; ++q) d += (q < rd.p && g >= rd.first[q]) ? 1 : 0;
-            const u32 src = (u32)(__ldg(&ptuples[g].y) >> 32);
-            rd.dst[d][(size_t)(g - rd.first[d]) * rec_words + w] = rec[(size_t)src * rec_words + w];
+        for (int k = 0; k < 4; ++k) {
+            const u64 w = 4 * c + k;
+            ok[k] = w >= a && w - a < nwords;
+            val[k] = 0;
+            if (ok[k]) {
+                val[k] = rec[(size_t)src * rec_words + ww];
+                if (++ww == rec_words) { ww = 0; ++j; src = j < cnt ? (u32)(__ldg(&ptuples[j].y) >> 32) : 0u; }
+            }
+        }
+        if (ok[0] && ok[3]) dst4[c] = make_uint4(val[0], val[1], val[2], val[3]);
+        else {
+            u32* q = reinterpret_cast<u32*>(dst4 + c);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (ok[k]) q[k] = val[k];
         }
     }
+    (void)inv;
 }
 
 int sort_records_local(tg_ctx* ctx, const tg_key_desc* desc, const tg_key_desc& tdesc, const void* d_rec, size_t n, void** out_dptr) {
@@ -669,32 +686,32 @@ int sort_records_impl(tg_ctx* ctx, const tg_key_desc* desc, void* d_in, size_t n
     if (h_ctl[3]) return tg_set_error(ctx, TG_ERR_TOO_LARGE, "sort: a worker holds 2^30 or more records");
     if (h_ctl[1] == 0) { *out_dptr = nullptr; *out_n = 0; return TG_OK; }
     TG_TRY(xwin_ensure(ctx, need));
-    RecDest rd;
-    rd.p = p;
-    u64 acc = 0;
-    for (int d = 0; d < TG_MAX_RANKS; ++d) {
-        rd.first[d] = (u32)acc;
-        if (d < p) acc += xr.send_cnt[d];
-        rd.dst[d] = nullptr;
-    }
-    rd.first[TG_MAX_RANKS] = (u32)acc;
+    u64 first[TG_MAX_RANKS + 1];                 // first tuple of every destination in the partitioned tuple array
+    first[0] = 0;
+    for (int d = 0; d < TG_MAX_RANKS; ++d) first[d + 1] = first[d] + (d < p ? xr.send_cnt[d] : 0);
     const int xprof = ctx->profile ? tg_prof_begin(ctx, TG_K_EXCHANGE) : -1;
     if (ctx->xwin.mode == 1) {
         u64 before[TG_MAX_RANKS];
         xchg_recv_offsets(ctx, before);
-        for (int d = 0; d < p; ++d) rd.dst[d] = (u32*)((char*)ctx->xwin.peer[d] + before[d] * rb);
-        if (n) TG_LAUNCH(ctx, scatter_records_kernel, ctx->sm_count * 8, 256, 0, (const u32*)d_in, (const ulonglong2*)d_ptup, (u32)n, rb / 4, (u32)(0xffffffffu / (rb / 4)) + 1, rd);
+        for (int d = 0; d < p; ++d) {
+            u32* dst = (u32*)((char*)ctx->xwin.peer[d] + before[d] * rb);
+            if (xr.send_cnt[d])
+                TG_LAUNCH(ctx, scatter_records_kernel, ctx->sm_count * 8, 256, 0, (const u32*)d_in, (const ulonglong2*)d_ptup + first[d],
+                          (u32)xr.send_cnt[d], rb / 4, 0u, dst);
+        }
         TG_TRY(xwin_barrier(ctx));
     }
     else {
         char* d_send;
         TG_TRY(tg_ws_get(ctx, WS_XCHG_SEND, (n + 1) * (size_t)rb, (void**)&d_send));
-        for (int d = 0; d < p; ++d) rd.dst[d] = (u32*)(d_send + (size_t)rd.first[d] * rb);
-        if (n) TG_LAUNCH(ctx, scatter_records_kernel, ctx->sm_count * 8, 256, 0, (const u32*)d_in, (const ulonglong2*)d_ptup, (u32)n, rb / 4, (u32)(0xffffffffu / (rb / 4)) + 1, rd);
+        for (int d = 0; d < p; ++d)
+            if (xr.send_cnt[d])
+                TG_LAUNCH(ctx, scatter_records_kernel, ctx->sm_count * 8, 256, 0, (const u32*)d_in, (const ulonglong2*)d_ptup + first[d],
+                          (u32)xr.send_cnt[d], rb / 4, 0u, (u32*)(d_send + (size_t)first[d] * rb));
         TG_NCCL(ctx, ncclGroupStart());
         u64 roff = 0;
         for (int r = 0; r < p; ++r) {
-            if (xr.send_cnt[r]) TG_NCCL(ctx, ncclSend(d_send + (size_t)rd.first[r] * rb, xr.send_cnt[r] * rb, ncclUint8, r, ctx->comm, ctx->stream));
+            if (xr.send_cnt[r]) TG_NCCL(ctx, ncclSend(d_send + (size_t)first[r] * rb, xr.send_cnt[r] * rb, ncclUint8, r, ctx->comm, ctx->stream));
             if (xr.recv_cnt[r]) TG_NCCL(ctx, ncclRecv((char*)ctx->xwin.base + roff * rb, xr.recv_cnt[r] * rb, ncclUint8, r, ctx->comm, ctx->stream));
             roff += xr.recv_cnt[r];
         }
