@@ -693,7 +693,10 @@ int sort_records_impl(tg_ctx* ctx, const tg_key_desc* desc, void* d_in, size_t n
     if (ctx->xwin.mode == 1) {
         u64 before[TG_MAX_RANKS];
         xchg_recv_offsets(ctx, before);
-        for (int d = 0; d < p; ++d) {
+        // one launch per destination, every worker starting with its right-hand neighbour: at any time each window is written by
+        // one peer (all workers going through the destinations in the same order would queue up on one NVLink ingress after the other)
+        for (int k = 0; k < p; ++k) {
+            const int d = (me + 1 + k) % p;
             u32* dst = (u32*)((char*)ctx->xwin.peer[d] + before[d] * rb);
             if (xr.send_cnt[d])
                 TG_LAUNCH(ctx, scatter_records_kernel, ctx->sm_count * 8, 256, 0, (const u32*)d_in, (const ulonglong2*)d_ptup + first[d],
@@ -718,7 +721,6 @@ int sort_records_impl(tg_ctx* ctx, const tg_key_desc* desc, void* d_in, size_t n
         TG_NCCL(ctx, ncclGroupEnd());
     }
     if (xprof >= 0) tg_prof_end(ctx, xprof);
-    (void)me;
     // ReceiveItems + SortAndWriteToFile (:665-742) on the received records (grouped by source worker in worker order)
     TG_TRY(sort_records_local(ctx, desc, tdesc, ctx->xwin.base, xr.n_recv, out_dptr));
     *out_n = (size_t)xr.n_recv;
