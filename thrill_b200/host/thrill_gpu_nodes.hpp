@@ -212,32 +212,6 @@ private:
     std::vector<tg_block> blocks_;
 };
 
-//! allocate ByteBlocks with BlockWriter's geometry, let the GPU result land in them, append them to `out`
-inline void FetchIntoFile(tg_ctx* c, Context& ctx, size_t num_items, uint32_t item_bytes,
-                          thrill::data::File& out) {
-    size_t nblocks = tg_file_geometry(num_items, item_bytes, thrill::data::start_block_size,
-                                      thrill::data::default_block_size, nullptr, 0);
-    std::vector<tg_block_geom> geom(nblocks);
-    tg_file_geometry(num_items, item_bytes, thrill::data::start_block_size,
-                     thrill::data::default_block_size, geom.data(), geom.size());
-    std::vector<thrill::data::PinnedByteBlockPtr> bytes;
-    std::vector<tg_block_mut> targets;
-    bytes.reserve(nblocks);
-    for (const tg_block_geom& g : geom) {
-        // power-of-two ByteBlock of at least g.bytes, as BlockWriter::AllocateBlock requests them
-        size_t cap = thrill::data::start_block_size;
-        while (cap < g.bytes) cap *= 2;
-        bytes.emplace_back(ctx.block_pool().AllocateByteBlock(cap, ctx.local_worker_id()));
-        targets.push_back(tg_block_mut { bytes.back()->data(), static_cast<size_t>(g.bytes) });
-    }
-    Check(c, tg_fetch_output(c, targets.data(), targets.size()), "tg_fetch_output");
-    for (size_t i = 0; i < nblocks; ++i) {
-        thrill::data::PinnedBlock pb(std::move(bytes[i]), 0, geom[i].bytes, geom[i].first_item,
-                                     geom[i].num_items, /* typecode_verify */ false);
-        out.AppendBlock(std::move(pb).MoveToBlock());
-    }
-}
-
 /******************************************************************************/
 // GPU node -> GPU node hand-off without the PCIe round trip
 
