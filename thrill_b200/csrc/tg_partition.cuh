@@ -191,15 +191,17 @@ __device__ __forceinline__ void rank_rows(const Item (&key)[ITEMS], u32 (&rank)[
 // takes its rank from a shared-memory atomic on its digit's warp-private counter (two 16-bit counters per 32-bit word).  One
 // ATOMS on the ADU pipe replaces the 28-instruction ballot match and the counter read/write on the ALU pipe, the busiest one
 // of this kernel (profiles/r2_partition_pass_u64.txt).
-template <int ITEMS, class Item, class DigitFn>
-__device__ __forceinline__ void rank_rows_unstable(const Item (&key)[ITEMS], u32 (&rank)[ITEMS], const DigitFn& fn, u32 whist_w) {
+template <bool STORE, int ITEMS, class Item, class DigitFn>
+__device__ __forceinline__ void rank_rows_unstable(const Item (&key)[ITEMS], u32 (&rank)[ITEMS], const DigitFn& fn, u32 whist_w,
+                                                   u32 pos0, u32 tile_base) {
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
-        const u32 d = fn(key[i], 0);
+        const u32 d = fn(key[i], tile_base + pos0 + i * 32);
         const u32 sh = (d & 1u) << 4;
         u32 old;
         asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(whist_w + (d >> 1) * 4u), "r"(1u << sh) : "memory");
         rank[i] = (old >> sh) & 0xffffu;
+        if (STORE) rank[i] |= d << 16;
     }
 }
 
@@ -365,7 +367,7 @@ partition_kernel(const typename ItemT<WORDS>::type* __restrict__ in, typename It
         __syncwarp();
 
         // ---- stable rank inside the warp (partial tiles always carry the digit along: padding has none)
-        if (full_tile && UNSTABLE && !DigitFn::kStoreDigit) rank_rows_unstable(key, rank, fn, whist_w_a);
+        if (full_tile && UNSTABLE) rank_rows_unstable<DigitFn::kStoreDigit>(key, rank, fn, whist_w_a, wbase + lane, tile_base);
         else if (full_tile) rank_rows<true, DigitFn::kStoreDigit>(key, rank, fn, whist_w_a, wbase + lane, tile_base, tile_valid, lt, DBG && (dbg & 2));
         else rank_rows<false, true>(key, rank, fn, whist_w_a, wbase + lane, tile_base, tile_valid, lt);
         __syncthreads();      // all items are in registers (buf is free), all warp counters final

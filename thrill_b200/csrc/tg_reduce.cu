@@ -254,7 +254,7 @@ __device__ __forceinline__ u64 op_combine(int op, u64 a, u64 b) {
 }
 
 constexpr u32 AGG_MAX_UNIT = 1u << 16;             // longer segments are cut (their pieces are merged afterwards)
-constexpr u32 AGG_FLUSH_FILL = AGG_SLOTS * 3 / 4;  // the table is emitted early rather than filled beyond this
+constexpr u32 AGG_FLUSH_FILL = AGG_SLOTS * 7 / 8;  // the table is emitted early rather than filled beyond this
 
 // One unit = a run of records whose keys occur in no other unit (whole segments), or a piece of a very long segment
 // (`partial`: its aggregates are merged afterwards).  The unit is streamed through the table in rounds of AGG_UNIT
@@ -477,6 +477,7 @@ struct HotTable {
     u32 super_slot[HOT_SUPER];      // slot of super-hot key j
     unsigned char super_idx[HOT_SLOTS];   // 0xff, or j: this slot holds super-hot key j
     u32 nhot, threshold, nsuper, super_threshold;
+    u32 sample_distinct, pad0, pad1, pad2;      // distinct keys among the HOT_SAMPLES sampled records
 };
 
 // slot of the key with hash h in a hot table (hashes in shared memory), or -1.  Two probes without a branch back (at load
@@ -519,10 +520,14 @@ __global__ void __launch_bounds__(1024) hot_select_kernel(const u64* __restrict_
     for (int i = threadIdx.x; i < 256; i += 1024) hist[i] = 0;
     for (u32 s = threadIdx.x; s < HOT_SLOTS; s += 1024) ht->super_idx[s] = 0xff;
     __syncthreads();
+    u32 seen = 0;
     for (u32 s = threadIdx.x; s < HOT_STAB; s += 1024) {
         const u32 c = scnt[s];
+        seen += c ? 1u : 0u;
         if (c >= HOT_MIN_COUNT) atomicAdd(&hist[c < 255 ? c : 255], 1u);
     }
+    seen = __reduce_add_sync(0xffffffffu, seen);
+    if ((threadIdx.x & 31) == 0 && seen) atomicAdd(&ht->sample_distinct, seen);
     __syncthreads();
     if (threadIdx.x == 0) {
         u32 acc = 0, t = 256, t2 = 256;
@@ -675,6 +680,15 @@ __global__ void __launch_bounds__(256) build_units_kernel(const u32* __restrict_
 
 int run_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 m, void* d_out, u64* out_distinct);
 
+// The aggregation does not depend on the order of the records inside a segment (the reduce functions are commutative and
+// associative as far as the reference's own arrival order is concerned): the two hash passes rank with the cheaper unstable
+// atomic ranking (TG_REDUCE_UNSTABLE=0 switches it off).
+bool reduce_unstable() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("TG_REDUCE_UNSTABLE"); on = e ? atoi(e) : 1; }
+    return on != 0;
+}
+
 // n records -> distinct keys in d_out (capacity n + 1)
 int run_partitioned_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 n, void* d_out, u64* out_distinct) {
     if (n < AGG_MIN_ITEMS || n >= (1u << 30) || getenv("TG_REDUCE_HBM_TABLE")) return run_aggregate(ctx, op, d_in, n, d_out, out_distinct);
@@ -725,10 +739,13 @@ int run_partitioned_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 n, void
         TG_TRY(tg_ws_get(ctx, WS_SORT_STATUS, (size_t)ctotal * RADIX * 4, (void**)&cstatus));
         TG_CUDA(ctx, cudaMemsetAsync(cstatus, 0, (size_t)ctotal * RADIX * 4, ctx->stream));
         SegList csl = { d_ctiles, chunkbase, ctotal, nullptr };
-        TG_TRY((launch_partition_seg<2, HotLevelDigit>(ctx, d_in, bufA, (u32)n, fn1, cstatus, csl)));
+        if (reduce_unstable()) TG_TRY((launch_partition_seg_unstable<2, HotLevelDigit>(ctx, d_in, bufA, (u32)n, fn1, cstatus, csl)));
+        else TG_TRY((launch_partition_seg<2, HotLevelDigit>(ctx, d_in, bufA, (u32)n, fn1, cstatus, csl)));
     }
     u32* h_tot1 = (u32*)ctx->pinned;
+    u32* h_hot = h_tot1 + RADIX;              // nhot, threshold, nsuper, super_threshold, sample_distinct
     TG_CUDA(ctx, cudaMemcpyAsync(h_tot1, d_tot1, RADIX * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TG_CUDA(ctx, cudaMemcpyAsync(h_hot, &ht->nhot, 32, cudaMemcpyDeviceToHost, ctx->stream));
     TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const u64 n_hot = h_tot1[RADIX - 1];          // records folded by the counting read; the first pass left them out
     h_tot1[RADIX - 1] = 0;
@@ -752,10 +769,24 @@ int run_partitioned_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 n, void
     for (int i = 0; i < 4; ++i) dl.fn[i] = HashLevelDigit{ AGG_SHIFT2 };
     TG_TRY((launch_seg_count<2, HashLevelDigit>(ctx, bufA, sl, dl, segcount)));
     TG_LAUNCH(ctx, seg_scan_kernel, dim3(RADIX, 1), RADIX, 0, segcount, d_gbase1, 1, RADIX, segbase);
-    TG_TRY((launch_partition_seg<2, HashLevelDigit>(ctx, bufA, bufB, (u32)n, dl.fn[0], status, sl)));
+    if (reduce_unstable()) TG_TRY((launch_partition_seg_unstable<2, HashLevelDigit>(ctx, bufA, bufB, (u32)n, dl.fn[0], status, sl)));
+    else TG_TRY((launch_partition_seg<2, HashLevelDigit>(ctx, bufA, bufB, (u32)n, dl.fn[0], status, sl)));
     // (3) units of whole segments, built on the device from the segment table
     int group_log2 = 0;
     while (group_log2 < 16 && ((u64)(n_rest ? n_rest : 1) << (group_log2 + 1)) / (RADIX * RADIX) <= (u64)AGG_UNIT / 2) ++group_log2;
+    // Skewed inputs: a segment holds far fewer distinct keys than records, and a unit's cost is dominated by the sweep of its
+    // 4096-slot table and its barriers.  The sample tells how many distinct keys to expect (its distinct ratio overestimates the
+    // ratio inside a segment by about 2x: keys repeat more over 1167 records than over a 65536-record sample of 1.25e8): group
+    // segments until a unit is expected to hold ~1400 distinct keys (measured: groups of 2 segments 1.33 -> 1.16 ms, groups of 4 start
+    // to flush partial aggregates) (TG_REDUCE_GROUP=0 switches it off).
+    static const bool regroup = !(getenv("TG_REDUCE_GROUP") && atoi(getenv("TG_REDUCE_GROUP")) == 0);
+    if (regroup && use_hot && h_hot[4] > 0 && n_rest > 0) {
+        const double est_ratio = 0.6 * (double)h_hot[4] / (double)HOT_SAMPLES;
+        double target = 1400.0 / (est_ratio > 0.05 ? est_ratio : 0.05);
+        if (target > 4.0 * AGG_UNIT) target = 4.0 * AGG_UNIT;
+        const double per_seg = (double)n_rest / (double)(RADIX * RADIX);
+        while (group_log2 < 6 && per_seg * (double)(2u << group_log2) <= target) ++group_log2;
+    }
     const size_t max_units = (table_words >> group_log2) + n / AGG_MAX_UNIT + 2;
     uint2* d_units;
     TG_TRY(tg_ws_get(ctx, WS_SEG_TILES2, max_units * sizeof(uint2) + 64, (void**)&d_units));
