@@ -191,6 +191,14 @@ int tg_hash_aggregate(tg_ctx* ctx, const tg_kv_desc* desc, const void* d_in, siz
 int tg_hash_partition(tg_ctx* ctx, const tg_kv_desc* desc, const void* d_in, size_t n, uint32_t p,
                       void* d_out, uint64_t* out_counts);
 
+/* The arithmetic of one exchange, pure host code (what every rank derives from the all-gathered p x p count matrix; exported so
+ * that the N > 1 host logic is testable without GPUs): counts[src * p + dst] = items rank src holds for rank dst.  For rank `me`:
+ * send_cnt[d], recv_cnt[s], recv_before[d] = items of the ranks below `me` in rank d's window (where this rank's share starts),
+ * *n_recv = items this rank receives, *worst = the largest receive size of ANY rank (window growth and TG_ERR_TOO_LARGE are
+ * decided on it, identically everywhere).  Replaces the per-(src,dst) block headers of the MixStream (data/multiplexer_header.hpp:36-72). */
+int tg_exchange_plan(uint32_t p, uint32_t me, const uint32_t* counts, uint64_t* send_cnt, uint64_t* recv_cnt,
+                     uint64_t* recv_before, uint64_t* n_recv, uint64_t* worst);
+
 /* ---- operator-level entry points -------------------------------------------------------------------- */
 
 /* Whole SortNode::MainOp + PushData (api/sort.hpp:537-663, :216-271) on device-resident items:

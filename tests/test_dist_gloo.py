@@ -183,3 +183,50 @@ def test_bench_parity_helpers_match_the_oracle():
     for p in (1, 2, 3, 8, 13):
         assert np.array_equal(bench.hash128to64_np(keys) % np.uint64(p), O.hash_partition_ids(keys, p).astype(np.uint64))
     assert np.array_equal(bench.zipf_cdf_numpy(4096), O.zipf_cdf(4096))
+
+
+def _plan_worker(rank, world, port, out_dir):
+    """every rank computes its part of the exchange plan with the PRODUCT's arithmetic (tg_exchange_plan of libthrill_gpu.so,
+    pure host code) from the all-gathered count matrix, as the GPU operators do after their ncclAllGather"""
+    import ctypes as C
+    import torch.distributed as dist
+    from thrill_b200 import capi
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rs = np.random.RandomState(100 + rank)
+    mine = rs.randint(0, 1000, size=world).astype(np.uint32)           # items this rank holds for every destination
+    if rank == 1:
+        mine[0] = 0                                                     # an empty (src, dst) pair
+    rows = [None] * world
+    dist.all_gather_object(rows, mine)
+    mat = np.ascontiguousarray(np.stack(rows), dtype=np.uint32)
+    L = capi.lib()
+    send = (C.c_uint64 * world)(); recv = (C.c_uint64 * world)(); before = (C.c_uint64 * world)()
+    n_recv, worst = C.c_uint64(), C.c_uint64()
+    assert L.tg_exchange_plan(world, rank, mat.ctypes.data_as(C.POINTER(C.c_uint32)), send, recv, before, C.byref(n_recv), C.byref(worst)) == 0
+    np.save(os.path.join(out_dir, "plan%d.npy" % rank),
+            np.array([list(send), list(recv), list(before), [n_recv.value] * world, [worst.value] * world], dtype=np.uint64))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_exchange_plan_is_consistent_across_ranks(tmp_path, world):
+    """N > 1 host logic of the fused exchange on CPU (gloo): what rank s sends to d is what d expects from s, every window is tiled
+    without gaps or overlaps in rank order, and all ranks agree on the largest receive size (the uniform growth / error verdict)"""
+    mp.spawn(_plan_worker, args=(world, 29540 + world, str(tmp_path)), nprocs=world, join=True)
+    plans = [np.load(os.path.join(str(tmp_path), "plan%d.npy" % r)) for r in range(world)]
+    for s in range(world):
+        for d in range(world):
+            assert plans[s][0][d] == plans[d][1][s]                     # send_cnt[s -> d] == recv_cnt[d <- s]
+    for d in range(world):
+        off = 0
+        for s in range(world):                                          # shares lie back to back in rank order
+            assert plans[s][2][d] == off
+            off += int(plans[s][0][d])
+        assert off == int(plans[d][3][0])                               # ... and fill exactly n_recv[d]
+    assert len({int(p[4][0]) for p in plans}) == 1
+    assert int(plans[0][4][0]) == max(int(p[3][0]) for p in plans)
+    from thrill_b200 import capi
+    assert capi.lib().tg_exchange_plan(0, 0, None, None, None, None, None, None) != 0

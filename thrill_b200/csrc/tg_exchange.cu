@@ -159,18 +159,8 @@ int xchg_counts(tg_ctx* ctx, const u32* d_totals, int item_bytes, XchgResult* re
     TG_NCCL(ctx, ncclAllGather(d_totals, d_mat, p, ncclUint32, ctx->comm, ctx->stream));
     TG_CUDA(ctx, cudaMemcpyAsync(h_mat, d_mat, (size_t)p * p * 4, cudaMemcpyDeviceToHost, ctx->stream));
     TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    u64 worst = 0;
-    for (int dst = 0; dst < p; ++dst) {
-        u64 tot = 0;
-        for (int src = 0; src < p; ++src) tot += h_mat[src * p + dst];
-        if (tot > worst) worst = tot;
-    }
-    res->n_recv = 0;
-    for (int r = 0; r < p; ++r) {
-        res->send_cnt[r] = h_mat[me * p + r];
-        res->recv_cnt[r] = h_mat[r * p + me];
-        res->n_recv += res->recv_cnt[r];
-    }
+    u64 worst = 0, before[TG_MAX_RANKS];
+    tg_exchange_plan((u32)p, (u32)me, h_mat, (uint64_t*)res->send_cnt, (uint64_t*)res->recv_cnt, (uint64_t*)before, (uint64_t*)&res->n_recv, (uint64_t*)&worst);
     if (worst >= (1u << 30))          // the same verdict on every rank: nobody is left waiting in a collective
         return tg_set_error(ctx, TG_ERR_TOO_LARGE, "exchange: a worker would receive %llu items (limit 2^30 - 1)", (unsigned long long)worst);
     *need_bytes_max = (worst + 4) * (u64)item_bytes;
@@ -184,12 +174,11 @@ int xchg_upload_dest(tg_ctx* ctx, int item_bytes, const XchgResult& res, void***
     const int p = ctx->nranks, me = ctx->rank;
     const u32* h_mat = (const u32*)ctx->pinned + 16384;
     u64* h_ptr = (u64*)ctx->pinned + 9216;      // byte offset 72 KB
-    u64 gbase = 0;
+    u64 gbase = 0, before[TG_MAX_RANKS], sc[TG_MAX_RANKS], rc[TG_MAX_RANKS], nr, worst;
+    tg_exchange_plan((u32)p, (u32)me, h_mat, (uint64_t*)sc, (uint64_t*)rc, (uint64_t*)before, (uint64_t*)&nr, (uint64_t*)&worst);
     for (int d = 0; d < PEER_MAX; ++d) {
         if (d >= p) { h_ptr[d] = 0; continue; }
-        u64 before = 0;
-        for (int src = 0; src < me; ++src) before += h_mat[src * p + d];
-        h_ptr[d] = (u64)(uintptr_t)ctx->xwin.peer[d] + (before - gbase) * (u64)item_bytes;      // (wraps like the pass's u32 positions do not: 64-bit)
+        h_ptr[d] = (u64)(uintptr_t)ctx->xwin.peer[d] + (before[d] - gbase) * (u64)item_bytes;   // (64-bit: wraps like the pass's positions)
         gbase += res.send_cnt[d];
     }
     TG_CUDA(ctx, cudaMemcpyAsync(ctx->xwin.d_peer, h_ptr, PEER_MAX * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
@@ -199,12 +188,9 @@ int xchg_upload_dest(tg_ctx* ctx, int item_bytes, const XchgResult& res, void***
 
 // after xchg_counts: this worker's items start at item before[d] of worker d's window
 void xchg_recv_offsets(tg_ctx* ctx, u64* before) {
-    const int p = ctx->nranks, me = ctx->rank;
     const u32* h_mat = (const u32*)ctx->pinned + 16384;
-    for (int d = 0; d < p; ++d) {
-        before[d] = 0;
-        for (int src = 0; src < me; ++src) before[d] += h_mat[src * p + d];
-    }
+    u64 sc[TG_MAX_RANKS], rc[TG_MAX_RANKS], nr, worst;
+    tg_exchange_plan((u32)ctx->nranks, (u32)ctx->rank, h_mat, (uint64_t*)sc, (uint64_t*)rc, (uint64_t*)before, (uint64_t*)&nr, (uint64_t*)&worst);
 }
 
 void xwin_release(tg_ctx* ctx) {
@@ -215,3 +201,24 @@ void xwin_release(tg_ctx* ctx) {
 }
 
 }  // namespace tgp
+
+extern "C" int tg_exchange_plan(uint32_t p, uint32_t me, const uint32_t* counts, uint64_t* send_cnt, uint64_t* recv_cnt,
+                                uint64_t* recv_before, uint64_t* n_recv, uint64_t* worst) {
+    if (p == 0 || p > TG_MAX_RANKS || me >= p || !counts) return TG_ERR_ARG;
+    u64 w = 0, nr = 0;
+    for (u32 dst = 0; dst < p; ++dst) {
+        u64 tot = 0, before = 0;
+        for (u32 src = 0; src < p; ++src) {
+            if (src < me) before += counts[src * p + dst];
+            tot += counts[src * p + dst];
+        }
+        if (tot > w) w = tot;
+        if (recv_before) recv_before[dst] = before;
+        if (send_cnt) send_cnt[dst] = counts[me * p + dst];
+        if (recv_cnt) recv_cnt[dst] = counts[dst * p + me];
+        nr += counts[dst * p + me];
+    }
+    if (n_recv) *n_recv = nr;
+    if (worst) *worst = w;
+    return TG_OK;
+}
