@@ -12,7 +12,7 @@
  * the operator + Size()).
  *
  * usage: THRILL_NET=mock THRILL_LOCAL=1 THRILL_WORKERS_PER_HOST=W \
- *        thrill_ref_driver op=<sort_u64|reduce_f64|reduce_u64|terasort> n=N [gen=uniform|zipf|file]
+ *        thrill_ref_driver op=<sort_u64|reduce_f64|reduce_u64|reduce_to_index|terasort|word_count> n=N [gen=uniform|zipf|file]
  *                          [in=path] [out=path] [iters=K] [seed=S] [universe=U] [exact=0|1]
  * Prints "RESULT op=... n=... workers=... hw_threads=... iter=i time=SECONDS" per iteration.
  ******************************************************************************/
@@ -22,11 +22,15 @@
 #include <thrill/api/gather.hpp>
 #include <thrill/api/generate.hpp>
 #include <thrill/api/read_binary.hpp>
+#include <thrill/api/read_lines.hpp>
 #include <thrill/api/reduce_by_key.hpp>
 #include <thrill/api/reduce_to_index.hpp>
 #include <thrill/api/size.hpp>
 #include <thrill/api/sort.hpp>
 #include <thrill/common/stats_timer.hpp>
+
+#include <examples/word_count/random_text_writer.hpp>
+#include <examples/word_count/word_count.hpp>
 
 #include <algorithm>
 #include <cmath>
@@ -291,6 +295,34 @@ int main(int argc, char** argv) {
                     }
                     report(it, timer.SecondsDouble());
                 }
+            }
+            else if (op == "word_count") {
+                // BASELINE.json configs[0] (plumbing): the reference's own examples/word_count/word_count.hpp on a text file (in=...)
+                // or on n lines of 10 random words each (random_text_writer.hpp, as word_count_run -g does); out = "word count" lines
+                using examples::word_count::WordCountPair;
+                common::StatsTimerStart timer;
+                std::vector<WordCountPair> all;
+                if (gen == "file") {
+                    all = examples::word_count::WordCount(api::ReadLines(ctx, in)).Gather(0);
+                }
+                else {
+                    std::default_random_engine rng(static_cast<unsigned>(seed));
+                    auto lines = api::Generate(ctx, n, [&](size_t) { return examples::word_count::RandomTextWriterGenerate(10, rng); });
+                    all = examples::word_count::WordCount(lines).Gather(0);
+                }
+                timer.Stop();
+                if (ctx.my_rank() == 0) {
+                    std::sort(all.begin(), all.end());
+                    size_t words = 0;
+                    for (auto& wc : all) words += wc.second;
+                    if (!out.empty()) {
+                        FILE* f = fopen(out.c_str(), "w");
+                        for (auto& wc : all) fprintf(f, "%s %zu\n", wc.first.c_str(), wc.second);
+                        fclose(f);
+                    }
+                    printf("WORDCOUNT distinct=%zu words=%zu\n", all.size(), words);
+                }
+                report(0, timer.SecondsDouble());
             }
             else {
                 if (ctx.my_rank() == 0) fprintf(stderr, "unknown op %s\n", op.c_str());

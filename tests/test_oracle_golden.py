@@ -183,3 +183,28 @@ def test_golden_r2_larger_cases_pin_the_oracle():
     red = O.reduce_simple(kv, O.OP_SUM_F64)
     assert len(red) == int(g["reduce_f64_exact_zipf_u2^20_4000000_distinct"])
     assert sha(red) == str(g["reduce_f64_exact_zipf_u2^20_4000000_sha256"])
+
+
+@pytest.mark.ref
+def test_cfg1_word_count_plumbing_two_loopback_workers(tmp_path):
+    """BASELINE.json configs[0]: the reference's own examples/word_count on ~1 MB of synthetic text with 2 local-loopback
+    workers (CPU reference, plumbing only: nothing of the GPU path is involved).  Run through oracle/_ref/thrill_ref_driver."""
+    import collections
+    import subprocess
+    if not O.have_ref_driver():
+        pytest.skip("oracle/_ref/thrill_ref_driver not built")
+    env = dict(os.environ, THRILL_NET="local", THRILL_LOCAL="2", THRILL_WORKERS_PER_HOST="1", THRILL_LOG="")
+    out = os.path.join(str(tmp_path), "wc.txt")
+    res = subprocess.run([O.REF_DRIVER, "op=word_count", "n=15000", "out=" + out], env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = [l for l in res.stdout.splitlines() if l.startswith("WORDCOUNT")][0]
+    assert "words=150000" in line and "workers=2" in res.stdout
+    counts = dict((w, int(c)) for w, c in (l.split() for l in open(out)))
+    assert sum(counts.values()) == 150000 and 900 <= len(counts) <= 1000
+    sample = "/root/reference/tests/inputs/wordcount.in"
+    if os.path.exists(sample):           # the reference's own fixture (tests/examples/word_count_test.cpp: 71 pairs), in this container only
+        res = subprocess.run([O.REF_DRIVER, "op=word_count", "gen=file", "in=" + sample, "out=" + out], env=env, capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0
+        got = dict((w, int(c)) for w, c in (l.split() for l in open(out)))
+        want = collections.Counter(open(sample).read().split())
+        assert got == dict(want) and len(got) == 71
