@@ -634,12 +634,21 @@ int launch_partition_seg(tg_ctx* ctx, const void* in, void* out, u32 n, const Di
 }
 
 // one segmented pass that need not be stable (see rank_rows_unstable); launch configurations 0-2, the others run the stable pass
+inline int unstable_cfg() {
+    static int cfg = -2;
+    if (cfg == -2) { const char* e = getenv("TG_UNSTABLE_CFG"); cfg = e ? atoi(e) : -1; }
+    return cfg;
+}
 template <int WORDS, class DigitFn>
 int launch_partition_seg_unstable(tg_ctx* ctx, const void* in, void* out, u32 n, const DigitFn& fn, u32* status, const SegList& sl) {
-    switch (sweep_cfg()) {
+    // TG_UNSTABLE_CFG = 8 / 9: the unstable passes alone without the TMA double buffer, 3 / 4 CTAs per SM (same 256 x 16 tile)
+    const int cfg = (unstable_cfg() >= 0 && (sweep_cfg() == 2 || sweep_cfg() == 1)) ? unstable_cfg() : sweep_cfg();
+    switch (cfg) {
     case 0: return launch_partition_v<WORDS, 512, 16, 1, DigitFn, true, false, true, false, true>(ctx, in, out, n, fn, nullptr, status, sl);
     case 1: return launch_partition_v<WORDS, 256, 16, 2, DigitFn, true, false, true, false, true>(ctx, in, out, n, fn, nullptr, status, sl);
     case 2: return launch_partition_v<WORDS, 256, 16, 3, DigitFn, true, false, true, false, true>(ctx, in, out, n, fn, nullptr, status, sl);
+    case 8: return launch_partition_v<WORDS, 256, 16, 3, DigitFn, true, false, false, false, true>(ctx, in, out, n, fn, nullptr, status, sl);
+    case 9: return launch_partition_v<WORDS, 256, 16, 4, DigitFn, true, false, false, false, true>(ctx, in, out, n, fn, nullptr, status, sl);
     default: return launch_partition_seg<WORDS, DigitFn>(ctx, in, out, n, fn, status, sl);
     }
 }
