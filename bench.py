@@ -521,10 +521,12 @@ def bench_reduce(args, ctx, world, rank, hbm_peak, peak_src, d_cdf, steps=None, 
 
     r_ms = []
     launches = 0
+    hot0 = 0
     for it in range(W + K):
         gen()
         if it == W:
             tg.profile_enable(True)
+            hot0 = int(L.tg_hot_records(tg.h))
         tg.barrier()
         l0 = tg.launches()
         tg.timer_start()
@@ -535,6 +537,7 @@ def bench_reduce(args, ctx, world, rank, hbm_peak, peak_src, d_cdf, steps=None, 
             r_ms.append(ms)
             launches += tg.launches() - l0
     part_list = tg.profile_list(capi.K_PARTITION)
+    hot_per_step = (int(L.tg_hot_records(tg.h)) - hot0) / float(K)       # records folded by the counting read, never moved
     prof = {name: tg.profile_get(cls) for name, cls in (("partition", capi.K_PARTITION), ("hist", capi.K_RADIX_HIST),
                                                         ("aggregate", capi.K_AGGREGATE), ("compact", capi.K_COMPACT),
                                                         ("segcount", capi.K_SEGCOUNT), ("exchange", capi.K_EXCHANGE),
@@ -564,16 +567,20 @@ def bench_reduce(args, ctx, world, rank, hbm_peak, peak_src, d_cdf, steps=None, 
     per_step = len(part_list) // K if K else 0
     full = [part_list[i * per_step + j] for i in range(K) for j in range(min(2, per_step))] if per_step else []
     launch_ms = sum(full) / len(full) if full else None
-    ach = REDUCE_PASS_BYTES_PER_RECORD * rn / (launch_ms / 1e3) / 1e9 if launch_ms else None
+    # algorithmic bytes of the two passes of a step: the first reads every record and writes those that were not folded, the
+    # second reads and writes the rest; per launch = half of that
+    moved = rn - (hot_per_step if world == 1 else hot_per_step)       # (per rank: the counter is this rank's)
+    pass_bytes = (16.0 * rn + 16.0 * moved + 32.0 * moved) / 2.0
+    ach = pass_bytes / (launch_ms / 1e3) / 1e9 if launch_ms else None
     traffic, traffic_src = profile_traffic("r2_partition_pass_kv16.txt")
     model_ach = REDUCE_MODEL_BYTES_PER_RECORD * rn / (r_step / 1e3) / 1e9
     agg_ms, agg_cnt = prof["aggregate"]
-    roofline = {"bound": "hbm", "kernel": "tgp::partition_kernel<2,256,8,3,HashLevelDigit,SEG> (one stable hash-digit pass: read 16 B + "
-                                          "write 16 B per record)",
+    roofline = {"bound": "hbm", "kernel": "tgp::partition_kernel<2,256,8,3,Hot/HashLevelDigit,SEG,unstable> (the two hash-digit passes of a step, averaged: "
+                                          "read 16 B + write 16 B per record that is moved; records of popular keys are only read)",
                 "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": (ach / hbm_peak) if ach else None, "peak_source": peak_src,
                 "traffic": traffic * (rn / 1.25e8) if traffic else None, "traffic_source": traffic_src,
-                "algorithmic_bytes_per_launch": REDUCE_PASS_BYTES_PER_RECORD * rn, "launch_ms": launch_ms,
-                "launches_timed": len(full),
+                "algorithmic_bytes_per_launch": pass_bytes, "launch_ms": launch_ms,
+                "launches_timed": len(full), "records_folded_by_the_counting_read_per_step": hot_per_step,
                 "operator_model": {"bytes_per_record": REDUCE_MODEL_BYTES_PER_RECORD, "what": "SURVEY.md 8(d) ReduceByKey total, Zipf(1, 2^26)",
                                    "achieved_GBps": model_ach, "frac": model_ach / hbm_peak},
                 "step_share": {"partition_ms": (part_ms - xchg_ms) / K, "partition_launches_per_step": (part_cnt - xchg_cnt) / K,

@@ -104,6 +104,9 @@ uint64_t tg_launch_count(const tg_ctx* ctx);
 /* how many local sorts on this ctx abandoned the prefix sort (top digits + finishing pass) for the plain LSD passes
  * because a run of equal key prefixes was too long (heavy duplicates); see tg_radix_sort_local */
 uint64_t tg_prefix_sort_fallbacks(const tg_ctx* ctx);
+/* records of popular keys that the aggregations on this ctx folded in their counting read, cumulative (such records are read once
+ * and never moved: bench.py needs the count for the algorithmic bytes of the hash passes) */
+uint64_t tg_hot_records(const tg_ctx* ctx);
 /* per-kernel-class device timing (CUDA events around every launch of the class while enabled):
  * bench.py's live roofline measurement.  tg_profile_get synchronises and returns the summed duration
  * and the number of launches of `kernel_class` since tg_profile_enable(ctx, 1). */

@@ -70,6 +70,7 @@ SYMBOLS = [
     ("tg_timer_stop", _i, [_vp, _P(C.c_float)]),
     ("tg_launch_count", _u64, [_vp]),
     ("tg_prefix_sort_fallbacks", _u64, [_vp]),
+    ("tg_hot_records", _u64, [_vp]),
     ("tg_profile_enable", _i, [_vp, _i]),
     ("tg_profile_get", _i, [_vp, _i, _P(C.c_float), _P(_u64)]),
     ("tg_profile_list", _i, [_vp, _i, _P(C.c_float), _sz, _P(_sz)]),

@@ -56,6 +56,7 @@ struct tg_ctx {
         void** d_peer = nullptr;               // device scratch: [0..p) destination base pointers of the current exchange
         int mode = -1;                         // -1 not negotiated yet, 0 = NCCL send/recv, 1 = P2P stores
     } xwin;
+    uint64_t hot_records = 0;                    // records folded by the counting reads of the aggregations (tg_hot_records)
     uint64_t bytes_h2d = 0, bytes_d2h = 0;       // through tg_upload(_blocks) / tg_download(_blocks)
     int spec_top_bit = 64;                     // prefix sort: expected position of the most significant varying key bit
     // result of the last *_file operator, fetched by tg_fetch_output

@@ -210,6 +210,7 @@ int tg_nranks(const tg_ctx* ctx) { return ctx->nranks; }
 void* tg_stream(const tg_ctx* ctx) { return (void*)ctx->stream; }
 uint64_t tg_launch_count(const tg_ctx* ctx) { return ctx->launches; }
 uint64_t tg_prefix_sort_fallbacks(const tg_ctx* ctx) { return ctx->prefix_sort_fallbacks; }
+uint64_t tg_hot_records(const tg_ctx* ctx) { return ctx->hot_records; }
 
 int tg_sync(tg_ctx* ctx) {
     TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

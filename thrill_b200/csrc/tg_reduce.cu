@@ -750,6 +750,7 @@ int run_partitioned_aggregate(tg_ctx* ctx, int op, const void* d_in, u64 n, void
     const u64 n_hot = h_tot1[RADIX - 1];          // records folded by the counting read; the first pass left them out
     h_tot1[RADIX - 1] = 0;
     const u64 n_rest = n - n_hot;
+    ctx->hot_records += n_hot;
     // (2) second hash digit inside the buckets of the first: segmented pass
     uint4* d_tiles;
     u32 total = 0;
