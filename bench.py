@@ -569,7 +569,7 @@ def bench_reduce(args, ctx, world, rank, hbm_peak, peak_src, d_cdf, steps=None, 
     launch_ms = sum(full) / len(full) if full else None
     # algorithmic bytes of the two passes of a step: the first reads every record and writes those that were not folded, the
     # second reads and writes the rest; per launch = half of that
-    moved = rn - (hot_per_step if world == 1 else hot_per_step)       # (per rank: the counter is this rank's)
+    moved = rn - hot_per_step                # (this rank's counter; at N > 1 it includes the few records folded in the post phase)
     pass_bytes = (16.0 * rn + 16.0 * moved + 32.0 * moved) / 2.0
     ach = pass_bytes / (launch_ms / 1e3) / 1e9 if launch_ms else None
     traffic, traffic_src = profile_traffic("r2_partition_pass_kv16.txt")
