@@ -98,3 +98,17 @@ def test_file_geometry_matches_blockwriter_restatement(n, ib, start, mx):
         assert geo[i].bytes == int(want[i]["end"])
         assert geo[i].num_items == int(want[i]["num_items"])
         assert geo[i].first_item == int(want[i]["first_item"])
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/thrill_gpu.h is the drop-in boundary: it must compile as C99 (no C++ types in the signatures) and link against
+    the shared library from a C program"""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "thrill_gpu.h"\nint main(void) { tg_dev_file f; tg_key_desc d; (void)f; (void)d; return tg_version() >= 100 ? 0 : 1; }\n')
+    exe = str(tmp_path / "hdr")
+    libdir = os.path.join(ROOT, "thrill_b200", "csrc")
+    res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                          "-L", libdir, "-lthrill_gpu", "-Wl,-rpath," + libdir, "-o", exe], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    assert subprocess.run([exe]).returncode == 0
