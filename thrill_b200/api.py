@@ -55,7 +55,13 @@ def bind_to_gpu_numa_node(device):
     try:
         import pynvml
         pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(device)
+        # NVML counts physical GPUs; CUDA ordinals go through CUDA_VISIBLE_DEVICES
+        vis = [v.strip() for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+        if vis and device < len(vis):
+            h = pynvml.nvmlDeviceGetHandleByUUID(vis[device]) if vis[device].startswith("GPU-") else \
+                pynvml.nvmlDeviceGetHandleByIndex(int(vis[device]))
+        else:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device)
         ncpu = os.cpu_count() or 1
         mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
         cpus = {i for i in range(ncpu) if (mask[i // 64] >> (i % 64)) & 1} & os.sched_getaffinity(0)
