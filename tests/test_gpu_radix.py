@@ -105,7 +105,8 @@ def test_radix_full_size_properties(ctx):
     ctx.ck(ctx.L.tg_radix_sort_local(ctx.h, C.byref(capi.u64_desc()), d, tmp, n))
     assert ctx.is_sorted(capi.u64_desc(), d, n)
     assert ctx.checksum(d, n, 8) == before
-    # spot-check against the oracle: the 4096 smallest keys of the first 2^22 generated keys' sort
+    # (sortedness + multiset equality is the full-size proof; the bit-exact comparison with the oracle / the reference's golden
+    # outputs is made at 1e6 and 1e7 keys in test_gpu_sort_kernels.py)
     head = ctx.download(d, 4096 * 8, np.uint64)
     assert np.all(head[1:] >= head[:-1])
     ctx.free(d); ctx.free(tmp)
