@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(1024) hot_select_kernel(const u64* __restrict_
     if ((threadIdx.x & 31) == 0 && seen) atomicAdd(&ht->sample_distinct, seen);
     __syncthreads();
     if (threadIdx.x == 0) {
-        u32 acc = 0, t = 256, t2 = 256;
+        u32 acc = 0, t = 256, t2 = 255;        // (t2: if even the keys seen >= 255 times outnumber HOT_SUPER, the first HOT_SUPER of them)
         for (int c = 255; c >= (int)HOT_MIN_COUNT; --c) {
             if (acc + hist[c] > HOT_CAP) break;
             acc += hist[c];
@@ -553,9 +553,11 @@ __global__ void __launch_bounds__(1024) hot_select_kernel(const u64* __restrict_
         ht->acc[slot] = ident;
         atomicAdd(&ht->nhot, 1u);
         if (c >= t2) {
-            const u32 j = atomicAdd(&ht->nsuper, 1u);          // (at most HOT_SUPER keys reach t2)
-            ht->super_slot[j] = slot;
-            ht->super_idx[slot] = (unsigned char)j;
+            const u32 j = atomicAdd(&ht->nsuper, 1u);
+            if (j < HOT_SUPER) {
+                ht->super_slot[j] = slot;
+                ht->super_idx[slot] = (unsigned char)j;
+            }
         }
     }
 }
@@ -636,7 +638,7 @@ __global__ void __launch_bounds__(HOT_HIST_THREADS) hot_hist_kernel(const ulongl
     if (hot) {
         for (int i = threadIdx.x; i < (int)HOT_SLOTS; i += blockDim.x)
             if (hhash[i] != 0 && hacc[i] != ident) op_apply(op, &ht->acc[i], hacc[i], false);
-        if (threadIdx.x < ht->nsuper) {
+        if (threadIdx.x < (ht->nsuper < HOT_SUPER ? ht->nsuper : HOT_SUPER)) {
             u64 a = ident;
             for (int w = 0; w < NW; ++w) a = op_combine(op, a, wacc[w * HOT_SUPER + threadIdx.x]);
             if (a != ident) op_apply(op, &ht->acc[ht->super_slot[threadIdx.x]], a, false);
