@@ -240,3 +240,17 @@ def test_r2_golden_reduce_4e6_zipf_exact(ctx):
     out = _aggregate(ctx, kv, capi.OP_SUM_F64)
     assert len(out) == int(g["reduce_f64_exact_zipf_u2^20_4000000_distinct"])
     assert sha(out) == str(g["reduce_f64_exact_zipf_u2^20_4000000_sha256"])
+
+
+@pytest.mark.parametrize("universe", [100, 700])
+def test_many_very_frequent_keys(ctx, universe):
+    """a small universe: every key is seen hundreds of times in the 65536-record sample, more keys than there are warp-private
+    accumulators (64) — all of them are folded by the counting read, some in the CTA-shared table; exact sums"""
+    from thrill_b200 import capi
+    n = 3000000
+    kv = O.gen_reduce_uniform(0, n, universe=universe, exact=1)
+    kv["key"][::1000] = 0                                    # the zero key (side slot) among them
+    out = _aggregate(ctx, kv, capi.OP_SUM_F64)
+    assert np.array_equal(out, O.reduce_simple(kv, O.OP_SUM_F64))
+    out = _aggregate(ctx, kv, capi.OP_MAX_F64)
+    assert np.array_equal(out, O.reduce_simple(kv, O.OP_MAX_F64))
